@@ -1,0 +1,143 @@
+/*
+ * b200align.h -- thin C ABI of libb200align.so, the Blackwell (sm_100a) replacement for the device side of
+ * MASA-CUDAlign's aligner extension.
+ *
+ * Path shorthand in the citations:  R/ = masa-cudalign-4.0.2.1028/,  C/ = R/libs/masa-core/src/.
+ *
+ * Two groups of entry points:
+ *
+ *  (1) "diag" primitives.  One call per protected virtual that reference CUDAligner implements for
+ *      AbstractDiagonalAligner (R/src/CUDAligner.hpp:216-232): the reference-side C++ adapter
+ *      (masa-cudalign_b200/host/B200Aligner.cpp) forwards each virtual to one of these, so MASA-Core's own
+ *      host policy (C/libmasa/aligners/AbstractDiagonalAligner.cpp:59-501) keeps deciding which rows, columns
+ *      and scores leave the aligner.  Used for stages 2/3 (goal matching, early stop) and as the
+ *      compatibility path of stage 1.
+ *
+ *  (2) b200_align_partition: the B200-first path.  The whole partition is aligned by one persistent kernel
+ *      (warp-per-strip chained wavefront, flag-gated borders in L2, on-device special-row area, exact
+ *      best-cell tracking); the results are the same artefacts the reference dispatches through IManager
+ *      (C/libmasa/IManager.hpp:98-313), delivered through the callbacks below after the kernel finishes.
+ *
+ * Conventions: all functions return 0 on success, non-zero on error (b200_last_error() describes it); no
+ * exceptions, no torch types, plain pointers and sizes.  Cells are the reference's cell_t
+ * (C/libmasa/libmasaTypes.hpp:35-41): a cell travelling in a ROW carries (H,F), in a COLUMN (H,E).
+ * Coordinates are 0-based indices relative to the pointers given to b200_set_sequences, exactly like the
+ * Partition the reference hands to IAligner::alignPartition (C/common/AlignerManager.cpp:165,177).
+ * Scores: match +1, mismatch -3, gap open 3, gap extend 2 (R/src/CUDAligner.hpp:77-98) -- compile-time, as
+ * in the reference (variable_penalties = NOT_SUPPORTED, R/src/CUDAligner.cpp:102).
+ */
+#ifndef B200ALIGN_H
+#define B200ALIGN_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_INF 999999999            /* C/libmasa/libmasaTypes.hpp:46 */
+
+#define B200_SMITH_WATERMAN 1         /* C/libmasa/IManager.hpp SMITH_WATERMAN   */
+#define B200_NEEDLEMAN_WUNSCH 2       /* C/libmasa/IManager.hpp NEEDLEMAN_WUNSCH */
+
+/* first row / first column sources (C/common/io/InitialCellsReader.cpp:84-108, CellsReader types) */
+#define B200_INIT_ZEROES 0            /* h = 0,                   e/f = -INF */
+#define B200_INIT_GAPS 1              /* h = -ext*pos - open,     e/f = -INF; pos 0 -> h = 0 */
+#define B200_INIT_GAPS_OPENED 2       /* h = -ext*pos,            e/f = -INF */
+#define B200_INIT_CUSTOM 3            /* cells supplied by the caller */
+
+/* kernel selection */
+#define B200_KERNEL_AUTO 0
+#define B200_KERNEL_S32 1             /* exact int32 lanes, byte compare: any alphabet, any border values */
+#define B200_KERNEL_S16X2 2           /* packed s16x2 DPX lanes with per-block rebasing; ACGT only */
+
+typedef struct { int h; int x; } b200_cell;          /* == cell_t: x is F in rows, E in columns */
+typedef struct { int score; int i; int j; } b200_score;   /* == score_t, 0-based (C/libmasa/libmasaTypes.hpp:88-95) */
+typedef struct { int found; int k; int score; int type; } b200_match;   /* == match_result_t (:51-60) */
+
+typedef struct {
+	int device;            /* CUDA device ordinal (reference: --gpu, R/src/CUDAlignerParameters.cpp:33-54) */
+	int kernel;            /* B200_KERNEL_* */
+	int warps_per_sm;      /* resident strip-warps per SM for the persistent kernel; 0 = default */
+	int reserved[5];
+} b200_config;
+
+typedef struct {
+	int i0, j0, i1, j1;          /* rows [i0,i1) of seq0, columns [j0,j1) of seq1 (Partition.hpp) */
+	int recurrence;              /* B200_SMITH_WATERMAN | B200_NEEDLEMAN_WUNSCH (IManager::getRecurrenceType) */
+	int first_row_init;          /* B200_INIT_* (IManager::getFirstRowInitType)    */
+	int first_col_init;          /* B200_INIT_* (IManager::getFirstColumnInitType) */
+	int special_row_interval;    /* IManager::getSpecialRowInterval; <=0 disables special rows */
+	int block_height;            /* row granularity of the special-row policy: 4*min(128,width) in the reference
+	                                (R/src/CUDAligner.cpp:295-297); 0 = that default */
+	int want_special_rows;       /* IManager::mustDispatchSpecialRows */
+	int want_last_row;           /* IManager::mustDispatchLastRow     */
+	int want_last_column;        /* IManager::mustDispatchLastColumn  */
+	int want_best_score;         /* IManager::mustDispatchScores: exact best cell of the partition */
+	int prune;                   /* IManager::mustPruneBlocks */
+	int super_i1, super_j1;      /* IManager::getSuperPartition: bounds used by the pruning test */
+	int reserved[4];
+} b200_partition;
+
+/* Callbacks == the IManager methods the reference aligner calls (C/libmasa/IManager.hpp:150-313).
+ * Buffers passed to dispatch_* are borrowed for the duration of the call. May be NULL when not needed. */
+typedef struct {
+	void* ctx;
+	void (*receive_first_row)(void* ctx, b200_cell* buffer, int len);
+	void (*receive_first_column)(void* ctx, b200_cell* buffer, int len);
+	void (*dispatch_row)(void* ctx, int i, const b200_cell* buffer, int len);
+	void (*dispatch_column)(void* ctx, int j, const b200_cell* buffer, int len);
+	void (*dispatch_score)(void* ctx, b200_score score);
+	int  (*must_continue)(void* ctx);
+} b200_callbacks;
+
+typedef struct {
+	b200_score best;             /* lexicographically smallest (i,j) among maximal cells, or score=-INF */
+	long long cells;             /* DP cells actually computed (pruned blocks excluded) */
+	long long cells_total;       /* (i1-i0)*(j1-j0) */
+	double device_ms;            /* CUDA-event time of the alignment kernels */
+	int strips;                  /* strip jobs executed */
+	int kernel_launches;         /* kernels launched by this call */
+	int kernel_used;             /* B200_KERNEL_S32 | B200_KERNEL_S16X2 */
+	int reserved[5];
+} b200_result;
+
+typedef struct b200_handle b200_handle;
+
+/* lifetime (IAligner::initialize / finalize, R/src/CUDAligner.cpp:137-164,579-586) */
+int b200_create(const b200_config* cfg, b200_handle** out);
+void b200_destroy(b200_handle* h);
+const char* b200_last_error(const b200_handle* h);      /* h may be NULL: error of the last failed b200_create */
+int b200_device_count(void);                             /* --list-gpus (R/src/CUDAlignerParameters.cpp) */
+
+/* IAligner::setSequences / unsetSequences (R/src/CUDAligner.cpp:229-283): host pointers, uploaded here */
+int b200_set_sequences(b200_handle* h, const char* seq0, int seq0_len, const char* seq1, int seq1_len);
+int b200_unset_sequences(b200_handle* h);
+
+/* (2) B200-first whole-partition path (replaces the loop of AbstractDiagonalAligner.cpp:59-159 plus
+ *     R/src/CUDAligner.cu:745-1156 for partitions that need no early stop). */
+int b200_align_partition(b200_handle* h, const b200_partition* p, const b200_callbacks* cb, b200_result* out);
+
+/* (1) diag primitives: one per CUDAligner virtual (R/src/CUDAligner.hpp:216-232). */
+int b200_diag_begin(b200_handle* h, const b200_partition* p, int grid_width, const int* split /* grid_width+1 */,
+                    int block_height);                                             /* initializeDiagonals  */
+int b200_diag_set_first_row(b200_handle* h, const b200_cell* cells, int j, int len);    /* setFirstRow     */
+int b200_diag_set_first_column(b200_handle* h, const b200_cell* cells, int i, int len); /* setFirstColumn: cells[0]=diag, [1..block_height] */
+int b200_diag_process(b200_handle* h, int diagonal, int window_left, int window_right); /* processDiagonal */
+int b200_diag_get_row(b200_handle* h, int j, int len, b200_cell* out);     /* getSpecialRow / getLastRow   */
+int b200_diag_get_last_column(b200_handle* h, int i, int len, b200_cell* out);          /* getLastColumn   */
+int b200_diag_get_block_scores(b200_handle* h, b200_score* out /* grid_width */);       /* getBlockScores  */
+int b200_diag_clear_pruned(b200_handle* h, int j0, int j1);                             /* clearPrunedBlocks (busH <- -INF) */
+int b200_diag_end(b200_handle* h);                                                      /* finalizeDiagonals */
+
+/* IAligner::matchLastColumn (C/libmasa/utils/AlignerUtils.cpp:50-107): goal matching of a last-column chunk
+ * against a reversed special-row chunk; first k wins, match before gap. Runs on the device. */
+int b200_match_last_column(b200_handle* h, const b200_cell* buffer, const b200_cell* base, int len, int goal,
+                           b200_match* out);
+
+/* statistics (IAligner::getProcessedCells etc.) */
+long long b200_processed_cells(const b200_handle* h);
+long long b200_kernel_launches(const b200_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200ALIGN_H */

@@ -1,0 +1,259 @@
+"""ctypes binding of libb200align.so (the C ABI in include/b200align.h) for tests, bench.py and smoke().
+
+This is NOT the product's host layer -- that is the C++ adapter in host/ (B200Aligner, the drop-in for the
+reference's CUDAligner class, R/src/CUDAligner.cpp).  Python is only used to drive the library from pytest and
+from the benchmark.  There is no CPU fallback here: if the shared library is missing or no GPU is present the
+calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200align.so")
+
+INF = 999999999
+SMITH_WATERMAN, NEEDLEMAN_WUNSCH = 1, 2
+INIT_ZEROES, INIT_GAPS, INIT_GAPS_OPENED, INIT_CUSTOM = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_S32, KERNEL_S16X2 = 0, 1, 2
+
+CELL = np.dtype([("h", "<i4"), ("x", "<i4")])
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("kernel", C.c_int), ("warps_per_sm", C.c_int), ("reserved", C.c_int * 5)]
+
+
+class Partition(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "i0", "j0", "i1", "j1", "recurrence", "first_row_init", "first_col_init", "special_row_interval",
+        "block_height", "want_special_rows", "want_last_row", "want_last_column", "want_best_score", "prune",
+        "super_i1", "super_j1")] + [("reserved", C.c_int * 4)]
+
+
+class Score(C.Structure):
+    _fields_ = [("score", C.c_int), ("i", C.c_int), ("j", C.c_int)]
+
+
+class Match(C.Structure):
+    _fields_ = [("found", C.c_int), ("k", C.c_int), ("score", C.c_int), ("type", C.c_int)]
+
+
+class Result(C.Structure):
+    _fields_ = [("best", Score), ("cells", C.c_longlong), ("cells_total", C.c_longlong), ("device_ms", C.c_double),
+                ("strips", C.c_int), ("kernel_launches", C.c_int), ("kernel_used", C.c_int), ("reserved", C.c_int * 5)]
+
+
+RECV_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)
+DISP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_int)
+SCORE_FN = C.CFUNCTYPE(None, C.c_void_p, Score)
+CONT_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
+
+
+class Callbacks(C.Structure):
+    _fields_ = [("ctx", C.c_void_p), ("receive_first_row", RECV_FN), ("receive_first_column", RECV_FN),
+                ("dispatch_row", DISP_FN), ("dispatch_column", DISP_FN), ("dispatch_score", SCORE_FN),
+                ("must_continue", CONT_FN)]
+
+
+EXPORTS = [
+    "b200_create", "b200_destroy", "b200_last_error", "b200_device_count", "b200_set_sequences",
+    "b200_unset_sequences", "b200_align_partition", "b200_diag_begin", "b200_diag_set_first_row",
+    "b200_diag_set_first_column", "b200_diag_process", "b200_diag_get_row", "b200_diag_get_last_column",
+    "b200_diag_get_block_scores", "b200_diag_clear_pruned", "b200_diag_end", "b200_match_last_column",
+    "b200_processed_cells", "b200_kernel_launches",
+]
+
+_lib = None
+
+
+def load_library(path=None):
+    """Load libb200align.so (raises OSError when it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    lib = C.CDLL(path or LIB_PATH)
+    lib.b200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.b200_destroy.argtypes = [C.c_void_p]
+    lib.b200_destroy.restype = None
+    lib.b200_last_error.argtypes = [C.c_void_p]
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_set_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.b200_unset_sequences.argtypes = [C.c_void_p]
+    lib.b200_align_partition.argtypes = [C.c_void_p, C.POINTER(Partition), C.POINTER(Callbacks), C.POINTER(Result)]
+    lib.b200_diag_begin.argtypes = [C.c_void_p, C.POINTER(Partition), C.c_int, C.c_void_p, C.c_int]
+    lib.b200_diag_set_first_row.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.b200_diag_set_first_column.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.b200_diag_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.b200_diag_get_row.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.b200_diag_get_last_column.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.b200_diag_get_block_scores.argtypes = [C.c_void_p, C.c_void_p]
+    lib.b200_diag_clear_pruned.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.b200_diag_end.argtypes = [C.c_void_p]
+    lib.b200_match_last_column.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(Match)]
+    lib.b200_processed_cells.argtypes = [C.c_void_p]
+    lib.b200_processed_cells.restype = C.c_longlong
+    lib.b200_kernel_launches.argtypes = [C.c_void_p]
+    lib.b200_kernel_launches.restype = C.c_longlong
+    if path is None:
+        _lib = lib
+    return lib
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def _as_u8(seq):
+    if isinstance(seq, (bytes, bytearray)):
+        return np.frombuffer(bytes(seq), dtype=np.uint8)
+    return np.ascontiguousarray(seq, dtype=np.uint8)
+
+
+class Aligner:
+    """Thin OO wrapper over one b200_handle."""
+
+    def __init__(self, device=0, kernel=KERNEL_AUTO, warps_per_sm=0):
+        self.lib = load_library()
+        cfg = Config(device=device, kernel=kernel, warps_per_sm=warps_per_sm)
+        self.h = C.c_void_p()
+        rc = self.lib.b200_create(C.byref(cfg), C.byref(self.h))
+        if rc != 0:
+            raise B200Error("b200_create failed: " + self.lib.b200_last_error(None).decode())
+        self._seqs = None
+
+    def close(self):
+        if self.h:
+            self.lib.b200_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise B200Error(f"{what} failed: {self.lib.b200_last_error(self.h).decode()}")
+
+    def set_sequences(self, s0, s1):
+        a, b = _as_u8(s0), _as_u8(s1)
+        self._seqs = (a, b)
+        self._check(self.lib.b200_set_sequences(self.h, a.ctypes.data, a.size, b.ctypes.data, b.size), "b200_set_sequences")
+
+    def align_partition(self, i0=0, j0=0, i1=None, j1=None, recurrence=SMITH_WATERMAN, first_row_init=INIT_ZEROES,
+                        first_col_init=INIT_ZEROES, first_row=None, first_col=None, special_row_interval=0,
+                        block_height=0, want_special_rows=False, want_last_row=False, want_last_column=False,
+                        want_best_score=True, prune=False, use_callbacks=True):
+        """Run b200_align_partition.  first_row / first_col: CELL arrays INCLUDING the corner as element 0
+        (n+1 / m+1 cells), used when the init type is INIT_CUSTOM (or to feed gaps through the callback path)."""
+        a, b = self._seqs
+        i1 = a.size if i1 is None else i1
+        j1 = b.size if j1 is None else j1
+        part = Partition(i0=i0, j0=j0, i1=i1, j1=j1, recurrence=recurrence, first_row_init=first_row_init,
+                         first_col_init=first_col_init, special_row_interval=special_row_interval,
+                         block_height=block_height, want_special_rows=int(want_special_rows),
+                         want_last_row=int(want_last_row), want_last_column=int(want_last_column),
+                         want_best_score=int(want_best_score), prune=int(prune), super_i1=i1, super_j1=j1)
+        out = {"rows": {}, "row_first": {}, "last_column": [], "scores": []}
+        pos = {"row": 0, "col": 0}
+
+        def recv(kind, src):
+            def fn(_ctx, buf, n):
+                dst = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_int)), shape=(n * 2,)).view(CELL)
+                if src is not None:
+                    dst[:] = src[pos[kind]:pos[kind] + n]
+                else:
+                    p0 = pos[kind]
+                    k = np.arange(p0, p0 + n, dtype=np.int64)
+                    t = first_row_init if kind == "row" else first_col_init
+                    if t == INIT_ZEROES:
+                        dst["h"] = 0
+                    else:
+                        dst["h"] = np.where(k == 0, 0, -2 * k - (3 if t == INIT_GAPS else 0))
+                    dst["x"] = -INF
+                pos[kind] += n
+            return RECV_FN(fn)
+
+        def disp_row(_ctx, i, buf, n):
+            arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_int)), shape=(n * 2,)).view(CELL).copy()
+            out["rows"].setdefault(i, []).append(arr)
+
+        def disp_col(_ctx, j, buf, n):
+            arr = np.ctypeslib.as_array(C.cast(buf, C.POINTER(C.c_int)), shape=(n * 2,)).view(CELL).copy()
+            out["last_column"].append(arr)
+
+        def disp_score(_ctx, s):
+            out["scores"].append((s.score, s.i, s.j))
+
+        cbs = None
+        keep = []
+        if use_callbacks:
+            keep = [recv("row", first_row), recv("col", first_col), DISP_FN(disp_row), DISP_FN(disp_col),
+                    SCORE_FN(disp_score), CONT_FN(lambda _c: 1)]
+            cbs = Callbacks(None, *keep)
+        res = Result()
+        rc = self.lib.b200_align_partition(self.h, C.byref(part), C.byref(cbs) if cbs is not None else None, C.byref(res))
+        self._check(rc, "b200_align_partition")
+        out["best"] = (res.best.score, res.best.i, res.best.j)
+        out["cells"] = res.cells
+        out["cells_total"] = res.cells_total
+        out["device_ms"] = res.device_ms
+        out["strips"] = res.strips
+        out["kernel_launches"] = res.kernel_launches
+        out["kernel_used"] = res.kernel_used
+        out["rows"] = {i: np.concatenate(v) for i, v in out["rows"].items()}
+        out["last_column"] = np.concatenate(out["last_column"]) if out["last_column"] else np.zeros(0, CELL)
+        return out
+
+    # ---- diag primitives -------------------------------------------------------------------------------
+    def diag_begin(self, part: Partition, split, block_height):
+        sp = np.ascontiguousarray(split, dtype=np.int32)
+        self._check(self.lib.b200_diag_begin(self.h, C.byref(part), sp.size - 1, sp.ctypes.data, block_height), "b200_diag_begin")
+
+    def diag_set_first_row(self, cells, j):
+        c = np.ascontiguousarray(cells, dtype=CELL)
+        self._check(self.lib.b200_diag_set_first_row(self.h, c.ctypes.data, j, c.size), "b200_diag_set_first_row")
+
+    def diag_set_first_column(self, cells, i, n):
+        c = np.ascontiguousarray(cells, dtype=CELL)
+        self._check(self.lib.b200_diag_set_first_column(self.h, c.ctypes.data, i, n), "b200_diag_set_first_column")
+
+    def diag_process(self, diagonal, wl, wr):
+        self._check(self.lib.b200_diag_process(self.h, diagonal, wl, wr), "b200_diag_process")
+
+    def diag_get_row(self, j, n):
+        out = np.zeros(n, CELL)
+        self._check(self.lib.b200_diag_get_row(self.h, j, n, out.ctypes.data), "b200_diag_get_row")
+        return out
+
+    def diag_get_last_column(self, i, n):
+        out = np.zeros(n, CELL)
+        self._check(self.lib.b200_diag_get_last_column(self.h, i, n, out.ctypes.data), "b200_diag_get_last_column")
+        return out
+
+    def diag_get_block_scores(self, B):
+        out = np.zeros(B, np.dtype([("score", "<i4"), ("i", "<i4"), ("j", "<i4")]))
+        self._check(self.lib.b200_diag_get_block_scores(self.h, out.ctypes.data), "b200_diag_get_block_scores")
+        return out
+
+    def diag_clear_pruned(self, j0, j1):
+        self._check(self.lib.b200_diag_clear_pruned(self.h, j0, j1), "b200_diag_clear_pruned")
+
+    def diag_end(self):
+        self._check(self.lib.b200_diag_end(self.h), "b200_diag_end")
+
+    def match_last_column(self, buffer, base, goal):
+        bu = np.ascontiguousarray(buffer, dtype=CELL)
+        ba = np.ascontiguousarray(base, dtype=CELL)
+        m = Match()
+        self._check(self.lib.b200_match_last_column(self.h, bu.ctypes.data, ba.ctypes.data, bu.size, goal, C.byref(m)), "b200_match_last_column")
+        return dict(found=bool(m.found), k=m.k, score=m.score, type=m.type)
+
+    def processed_cells(self):
+        return self.lib.b200_processed_cells(self.h)
+
+    def kernel_launches(self):
+        return self.lib.b200_kernel_launches(self.h)

@@ -1,0 +1,666 @@
+// engine.cu -- host side of libb200align.so: device buffers, strip-job construction, kernel launches and the
+// C ABI declared in include/b200align.h.  No CPU fallback: every entry point fails loudly without a GPU.
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/b200align.h"
+#include "strip_common.cuh"
+#include "strip_s32.cuh"
+#include "strip_s16.cuh"
+
+using namespace b200;
+
+static_assert(sizeof(b200_cell) == sizeof(Cell), "cell layout");
+
+namespace {
+
+std::string g_create_error;
+
+template <class T>
+struct DevBuf {
+	T* p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 64;
+		cudaError_t e = cudaMalloc((void**)&p, want * sizeof(T));
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+struct PinBuf {
+	T* p = nullptr;
+	size_t cap = 0;
+	cudaError_t reserve(size_t n) {
+		if (n <= cap) return cudaSuccess;
+		if (p) cudaFreeHost(p);
+		p = nullptr; cap = 0;
+		size_t want = n + n / 8 + 64;
+		cudaError_t e = cudaMallocHost((void**)&p, want * sizeof(T));
+		if (e == cudaSuccess) cap = want;
+		return e;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct b200_handle {
+	b200_config cfg;
+	int sm_count = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	std::string err;
+
+	// sequences (device, 1 byte per base like the reference: R/src/cuda_util.cpp:50-56)
+	DevBuf<unsigned char> s0, s1;
+	int n0 = 0, n1 = 0;
+	bool acgt_only = false;
+
+	// strip machinery
+	DevBuf<Cell> busH, left, right, sra;
+	DevBuf<StripJob> jobs;
+	DevBuf<int> progress;
+	DevBuf<Score3> results;
+	DevBuf<int> scalars;            // [0] job counter, [1] global best, [2] stop flag, [4..5] cells (u64)
+	PinBuf<Cell> hcells;            // pinned staging for rows / columns
+	PinBuf<Score3> hresults;
+	PinBuf<int> hscalars;
+	std::vector<StripJob> hjobs;
+
+	// diag-mode state (R/src/CUDAligner.hpp:216-232 contract)
+	struct {
+		bool active = false;
+		b200_partition part;
+		int B = 0, bh = 0;
+		std::vector<int> split;
+		DevBuf<Cell> vbuf;          // [2][B+1][bh+1] vertical borders, ping-pong by diagonal parity
+		DevBuf<Cell> col0;          // [2][bh+1] first-column chunks (next / current)
+		int col0_cur = 0;
+		bool col0_valid[2] = {false, false};
+		int last_diag = -1;
+		std::vector<b200_score> scores;
+	} dg;
+
+	long long stat_cells = 0;
+	long long stat_launches = 0;
+};
+
+#define CU(h, call)                                                                                   \
+	do {                                                                                              \
+		cudaError_t e_ = (call);                                                                      \
+		if (e_ != cudaSuccess) {                                                                      \
+			(h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+			return 1;                                                                                 \
+		}                                                                                             \
+	} while (0)
+
+namespace {
+
+constexpr int kR32 = 16;             // rows per lane, s32 kernel  -> 512-row strips (== reference block height 4*128)
+constexpr int kSH32 = 32 * kR32;
+
+__global__ void fill_cells_kernel(Cell* dst, long long n, int type, int start_pos, int h_const) {
+	long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (k >= n) return;
+	Cell c;
+	c.x = -kInf;
+	if (type == B200_INIT_ZEROES) c.h = h_const;
+	else {
+		long long pos = start_pos + k;
+		c.h = (pos == 0) ? 0 : (int)(-kGapExt * pos - (type == B200_INIT_GAPS ? kGapOpen : 0));   // InitialCellsReader.cpp:84-108
+	}
+	dst[k] = c;
+}
+
+__global__ void fill_const_kernel(Cell* dst, long long n, int hv, int xv) {
+	long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (k < n) { dst[k].h = hv; dst[k].x = xv; }
+}
+
+__global__ void match_column_kernel(const Cell* buffer, const Cell* base, int len, int goal, int gap_open, int* out) {
+	// first k with H+H == goal, else E+E+open == goal, error if a sum exceeds the goal (AlignerUtils.cpp:59-84).
+	// out[0] = smallest k with any event, encoded as k*4 + kind (0 match, 1 gap, 2 err1, 3 err2); INT_MAX if none.
+	int k = blockIdx.x * blockDim.x + threadIdx.x;
+	int code = INT_MAX;
+	if (k < len) {
+		int sm = base[k].h + buffer[k].h;
+		int sg = base[k].x + buffer[k].x + gap_open;
+		if (sm == goal) code = k * 4 + 0;
+		else if (sg == goal) code = k * 4 + 1;
+		else if (sm > goal) code = k * 4 + 2;
+		else if (sg > goal) code = k * 4 + 3;
+	}
+	for (int d = 16; d >= 1; d >>= 1) code = min(code, __shfl_xor_sync(0xffffffffu, code, d));
+	if ((threadIdx.x & 31) == 0 && code != INT_MAX) atomicMin(out, code);
+}
+
+int grid_for(b200_handle* h, const void* kernel, int njobs) {
+	int per_sm = 0;
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, 0);
+	if (per_sm < 1) per_sm = 1;
+	if (h->cfg.warps_per_sm > 0) {
+		int lim = (h->cfg.warps_per_sm + kWarpsPerBlock - 1) / kWarpsPerBlock;
+		if (lim < per_sm) per_sm = lim;
+	}
+	int cap = per_sm * h->sm_count;                      // co-residency bound: required by the flag-chained strips
+	int need = (njobs + kWarpsPerBlock - 1) / kWarpsPerBlock;
+	return std::max(1, std::min(cap, need));
+}
+
+// Launch the strip kernel over h->hjobs (already uploaded to h->jobs).
+int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kernel_kind) {
+	StripParams sp;
+	sp.s0 = h->s0.p; sp.s1 = h->s1.p;
+	sp.busH = h->busH.p; sp.left = h->left.p; sp.right = h->right.p; sp.sra = h->sra.p;
+	sp.jobs = h->jobs.p; sp.njobs = njobs;
+	sp.job_counter = h->scalars.p + 0;
+	sp.global_best = h->scalars.p + 1;
+	sp.stop_flag = h->scalars.p + 2;
+	sp.cells_done = reinterpret_cast<unsigned long long*>(h->scalars.p + 4);
+	sp.progress = h->progress.p;
+	sp.results = h->results.p;
+	sp.recurrence = recurrence;
+	sp.track = track;
+	const bool sw = recurrence == B200_SMITH_WATERMAN;
+	const void* fn = nullptr;
+	if (kernel_kind == B200_KERNEL_S16X2) {
+		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16, true, true> : (const void*)strip_kernel_s16<kR16, true, false>;
+		else    fn = track ? (const void*)strip_kernel_s16<kR16, false, true> : (const void*)strip_kernel_s16<kR16, false, false>;
+	} else {
+		if (sw) fn = track ? (const void*)strip_kernel_s32<kR32, true, true> : (const void*)strip_kernel_s32<kR32, true, false>;
+		else    fn = track ? (const void*)strip_kernel_s32<kR32, false, true> : (const void*)strip_kernel_s32<kR32, false, false>;
+	}
+	int grid = grid_for(h, fn, njobs);
+	void* args[] = {(void*)&sp};
+	CU(h, cudaLaunchKernel(fn, dim3(grid), dim3(kWarpsPerBlock * 32), args, 0, h->stream));
+	h->stat_launches++;
+	return 0;
+}
+
+int reset_scalars(b200_handle* h, int global_best) {
+	CU(h, h->scalars.reserve(8));
+	CU(h, h->hscalars.reserve(8));
+	int* s = h->hscalars.p;
+	s[0] = 0; s[1] = global_best; s[2] = 0; s[3] = 0; s[4] = 0; s[5] = 0; s[6] = 0; s[7] = 0;
+	CU(h, cudaMemcpyAsync(h->scalars.p, s, 8 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	return 0;
+}
+
+int strip_height(int kernel_kind) { return kernel_kind == B200_KERNEL_S16X2 ? kSH16 : kSH32; }
+
+int pick_kernel(b200_handle* h, int requested) {
+	int k = requested ? requested : h->cfg.kernel;
+	if (k == B200_KERNEL_AUTO) k = h->acgt_only ? B200_KERNEL_S16X2 : B200_KERNEL_S32;
+	if (k == B200_KERNEL_S16X2 && !h->acgt_only) k = B200_KERNEL_S32;   // packed kernel needs 2-bit codes
+#ifdef B200_NO_S16
+	k = B200_KERNEL_S32;
+#endif
+	return k;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int b200_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+extern "C" const char* b200_last_error(const b200_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int b200_create(const b200_config* cfg, b200_handle** out) {
+	if (!out) return 1;
+	*out = nullptr;
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) + "); libb200align has no CPU fallback";
+		return 2;
+	}
+	b200_handle* h = new b200_handle();
+	memset(&h->cfg, 0, sizeof(h->cfg));
+	if (cfg) h->cfg = *cfg;
+	if (h->cfg.device < 0 || h->cfg.device >= ndev) h->cfg.device = h->cfg.device < 0 ? 0 : h->cfg.device % ndev;   // wrap like R/src/CUDAligner.cpp:142-148
+	if ((e = cudaSetDevice(h->cfg.device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return 3; }
+	cudaDeviceProp prop;
+	if ((e = cudaGetDeviceProperties(&prop, h->cfg.device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return 3; }
+	if (prop.major < 10) {
+		g_create_error = std::string("device ") + prop.name + " is not sm_100-class; this library ships sm_100a code only";
+		delete h; return 4;
+	}
+	h->sm_count = prop.multiProcessorCount;
+	if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
+		g_create_error = cudaGetErrorString(e); delete h; return 3;
+	}
+	*out = h;
+	return 0;
+}
+
+extern "C" void b200_destroy(b200_handle* h) {
+	if (!h) return;
+	cudaSetDevice(h->cfg.device);
+	cudaStreamSynchronize(h->stream);
+	h->s0.release(); h->s1.release(); h->busH.release(); h->left.release(); h->right.release(); h->sra.release();
+	h->jobs.release(); h->progress.release(); h->results.release(); h->scalars.release();
+	h->hcells.release(); h->hresults.release(); h->hscalars.release();
+	h->dg.vbuf.release(); h->dg.col0.release();
+	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
+	cudaStreamDestroy(h->stream);
+	delete h;
+}
+
+extern "C" long long b200_processed_cells(const b200_handle* h) { return h ? h->stat_cells : 0; }
+extern "C" long long b200_kernel_launches(const b200_handle* h) { return h ? h->stat_launches : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// sequences
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int b200_set_sequences(b200_handle* h, const char* seq0, int seq0_len, const char* seq1, int seq1_len) {
+	if (!h) return 1;
+	if (!seq0 || !seq1 || seq0_len < 0 || seq1_len < 0) { h->err = "b200_set_sequences: bad arguments"; return 1; }
+	CU(h, cudaSetDevice(h->cfg.device));
+	CU(h, h->s0.reserve((size_t)seq0_len + 64));
+	CU(h, h->s1.reserve((size_t)seq1_len + 64));
+	CU(h, cudaMemcpyAsync(h->s0.p, seq0, (size_t)seq0_len, cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaMemcpyAsync(h->s1.p, seq1, (size_t)seq1_len, cudaMemcpyHostToDevice, h->stream));
+	// alphabet scan (host, vectorisable): the packed kernel handles exactly A,C,G,T
+	auto only_acgt = [](const char* s, int n) {
+		unsigned char bad = 0;
+		for (int k = 0; k < n; k++) { unsigned char c = (unsigned char)s[k]; bad |= (unsigned char)!(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
+		return bad == 0;
+	};
+	h->acgt_only = only_acgt(seq0, seq0_len) && only_acgt(seq1, seq1_len);
+	h->n0 = seq0_len; h->n1 = seq1_len;
+	CU(h, h->busH.reserve((size_t)seq1_len + 64));
+	CU(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+extern "C" int b200_unset_sequences(b200_handle* h) {
+	if (!h) return 1;
+	h->n0 = h->n1 = 0;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (2) whole-partition path
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+// Row ids (number of rows above the special row, relative to i0) at which the reference flushes special rows:
+// AbstractDiagonalAligner::isSpecialRow (AbstractDiagonalAligner.cpp:466-478) with block height bh.
+void special_row_ids(int height, int bh, int interval, std::vector<int>& ids) {
+	ids.clear();
+	if (interval <= 0 || bh <= 0) return;
+	int fbi = (interval + bh - 1) / bh;
+	if (fbi <= 0) fbi = 1;
+	if (fbi <= 8192 / bh) fbi = 8192 / bh;
+	if (fbi <= 0) fbi = 1;
+	for (long long by = fbi; by * bh < height; by += fbi) ids.push_back((int)(by * bh));
+}
+
+}  // namespace
+
+extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, const b200_callbacks* cb, b200_result* out) {
+	if (!h) return 1;
+	if (!p || !out) { h->err = "b200_align_partition: bad arguments"; return 1; }
+	memset(out, 0, sizeof(*out));
+	const int m = p->i1 - p->i0, n = p->j1 - p->j0;
+	if (m <= 0 || n <= 0 || p->i0 < 0 || p->j0 < 0 || p->i1 > h->n0 || p->j1 > h->n1) { h->err = "b200_align_partition: partition outside the sequences"; return 1; }
+	CU(h, cudaSetDevice(h->cfg.device));
+	const int kind = pick_kernel(h, 0);
+	const int SH = strip_height(kind);
+	const bool sw = p->recurrence == B200_SMITH_WATERMAN;
+	const int track = p->want_best_score ? 2 : 0;
+
+	// ---- special rows and strips
+	int bh = p->block_height > 0 ? p->block_height : 4 * std::min(128, n);
+	std::vector<int> sr_ids;
+	if (p->want_special_rows) special_row_ids(m, bh, p->special_row_interval, sr_ids);
+	h->hjobs.clear();
+	{
+		size_t next_sr = 0;
+		int r = 0;
+		while (r < m) {
+			int end = std::min(m, r + SH);
+			long long sra_off = -1;
+			if (next_sr < sr_ids.size() && sr_ids[next_sr] <= end) {
+				end = sr_ids[next_sr];
+				sra_off = (long long)next_sr * n;
+				next_sr++;
+			}
+			StripJob j;
+			memset(&j, 0, sizeof(j));
+			j.i0 = p->i0 + r; j.rows = end - r; j.j0 = p->j0; j.cols = n;
+			j.dep = (int)h->hjobs.size() - 1;
+			j.flags = (p->first_col_init == B200_INIT_ZEROES) ? JOB_LEFT_ZERO : 0;
+			j.left_off = r;
+			j.right_off = p->want_last_column ? r : -1;
+			j.sra_off = sra_off;
+			h->hjobs.push_back(j);
+			r = end;
+		}
+	}
+	const int njobs = (int)h->hjobs.size();
+
+	// ---- buffers
+	CU(h, h->jobs.reserve(njobs));
+	CU(h, h->progress.reserve(njobs));
+	CU(h, h->results.reserve(njobs));
+	CU(h, h->hresults.reserve(njobs));
+	if (!sr_ids.empty()) CU(h, h->sra.reserve(sr_ids.size() * (size_t)n));
+	if (p->want_last_column) CU(h, h->right.reserve((size_t)m + 1));
+	size_t stage_cells = std::max<size_t>((size_t)std::max(m, n) + 1, 1024);
+	CU(h, h->hcells.reserve(stage_cells));
+	if (reset_scalars(h, sw ? 0 : -kInf)) return 1;
+	CU(h, cudaMemcpyAsync(h->jobs.p, h->hjobs.data(), njobs * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaMemsetAsync(h->progress.p, 0, njobs * sizeof(int), h->stream));
+
+	// ---- first row -> busH[j0..j1), first column -> left[0..m]   (AbstractDiagonalAligner.cpp:83-89,409-456)
+	Cell corner_col; corner_col.h = 0; corner_col.x = -kInf;
+	Cell corner_row = corner_col;
+	const bool have_cb = cb != nullptr;
+	if (have_cb && cb->receive_first_column) cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(&corner_col), 1);
+	if (have_cb && cb->receive_first_row) cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(&corner_row), 1);
+	Cell first_row_tail = corner_row;
+	if (p->first_row_init == B200_INIT_ZEROES || !(have_cb && cb->receive_first_row)) {
+		int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
+		fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1, 0);
+		h->stat_launches++;
+		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * n - (type == B200_INIT_GAPS ? kGapOpen : 0);
+	} else {
+		cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p), n);
+		first_row_tail = h->hcells.p[n - 1];
+		CU(h, cudaMemcpyAsync(h->busH.p + p->j0, h->hcells.p, (size_t)n * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+		CU(h, cudaStreamSynchronize(h->stream));
+	}
+	if (p->first_col_init != B200_INIT_ZEROES) {
+		CU(h, h->left.reserve((size_t)m + 1));
+		if (have_cb && cb->receive_first_column) {
+			h->hcells.p[0] = corner_col;
+			cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p + 1), m);
+			CU(h, cudaMemcpyAsync(h->left.p, h->hcells.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+			CU(h, cudaStreamSynchronize(h->stream));
+		} else {
+			int type = p->first_col_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_col_init;
+			fill_cells_kernel<<<(m + 1 + 255) / 256, 256, 0, h->stream>>>(h->left.p, (long long)m + 1, type, 0, 0);
+			h->stat_launches++;
+		}
+	}
+
+	// ---- the alignment itself: one persistent launch
+	CU(h, cudaEventRecord(h->ev0, h->stream));
+	if (launch_strips(h, njobs, p->recurrence, track, kind)) return 1;
+	CU(h, cudaEventRecord(h->ev1, h->stream));
+	if (track) CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
+	CU(h, cudaGetLastError());
+	float ms = 0;
+	CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+
+	out->device_ms = ms;
+	out->strips = njobs;
+	out->kernel_launches = 1;
+	out->kernel_used = kind;
+	out->cells_total = (long long)m * n;
+	out->cells = (long long)*reinterpret_cast<unsigned long long*>(h->hscalars.p + 4);
+	h->stat_cells += out->cells;
+
+	b200_score best; best.score = -kInf; best.i = -1; best.j = -1;
+	if (track) {
+		for (int k = 0; k < njobs; k++) {
+			const Score3& s = h->hresults.p[k];
+			if (s.i >= 0 && (s.score > best.score || (s.score == best.score && (s.i < best.i || (s.i == best.i && s.j < best.j))))) {
+				best.score = s.score; best.i = s.i; best.j = s.j;
+			}
+		}
+	}
+	out->best = best;
+
+	// ---- hand the artefacts to the caller in the reference's dispatch format
+	if (have_cb) {
+		auto first_col_cell = [&](int rows_above) {   // first-column cell of the row with `rows_above` rows above it, f = -INF
+			Cell c; c.h = 0; c.x = -kInf;
+			return c;
+		};
+		(void)first_col_cell;
+		// first-column H values for the first cell of each dispatched row
+		std::vector<int> sr_first_h(sr_ids.size(), 0);
+		int last_first_h = 0;
+		if (p->first_col_init != B200_INIT_ZEROES) {
+			for (size_t k = 0; k < sr_ids.size(); k++)
+				CU(h, cudaMemcpy(&sr_first_h[k], &h->left.p[sr_ids[k]].h, sizeof(int), cudaMemcpyDeviceToHost));
+			CU(h, cudaMemcpy(&last_first_h, &h->left.p[m].h, sizeof(int), cudaMemcpyDeviceToHost));
+		}
+		if (cb->dispatch_row) {
+			for (size_t k = 0; k < sr_ids.size(); k++) {
+				CU(h, cudaMemcpy(h->hcells.p, h->sra.p + k * (size_t)n, (size_t)n * sizeof(Cell), cudaMemcpyDeviceToHost));
+				b200_cell fc; fc.h = sr_first_h[k]; fc.x = -kInf;
+				cb->dispatch_row(cb->ctx, p->i0 + sr_ids[k], &fc, 1);
+				cb->dispatch_row(cb->ctx, p->i0 + sr_ids[k], reinterpret_cast<b200_cell*>(h->hcells.p), n);
+			}
+			if (p->want_last_row) {
+				CU(h, cudaMemcpy(h->hcells.p, h->busH.p + p->j0, (size_t)n * sizeof(Cell), cudaMemcpyDeviceToHost));
+				b200_cell fc; fc.h = last_first_h; fc.x = -kInf;
+				cb->dispatch_row(cb->ctx, p->i1, &fc, 1);
+				cb->dispatch_row(cb->ctx, p->i1, reinterpret_cast<b200_cell*>(h->hcells.p), n);
+			}
+		}
+		if (cb->dispatch_column && p->want_last_column) {
+			CU(h, cudaMemcpy(h->hcells.p, h->right.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyDeviceToHost));
+			b200_cell fc; fc.h = first_row_tail.h; fc.x = -kInf;
+			cb->dispatch_column(cb->ctx, p->j1, &fc, 1);
+			for (int r = 0; r < m; r += bh) {
+				int len = std::min(bh, m - r);
+				cb->dispatch_column(cb->ctx, p->j1, reinterpret_cast<b200_cell*>(h->hcells.p + 1 + r), len);
+				if (cb->must_continue && !cb->must_continue(cb->ctx)) break;
+			}
+		}
+		if (cb->dispatch_score && track && best.i >= 0) cb->dispatch_score(cb->ctx, best);
+	}
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (1) diag primitives
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int b200_diag_begin(b200_handle* h, const b200_partition* p, int grid_width, const int* split, int block_height) {
+	if (!h) return 1;
+	if (!p || !split || grid_width < 1 || block_height < 1) { h->err = "b200_diag_begin: bad arguments"; return 1; }
+	if (p->i0 < 0 || p->j0 < 0 || p->i1 > h->n0 || p->j1 > h->n1 || p->i1 <= p->i0 || p->j1 <= p->j0) { h->err = "b200_diag_begin: partition outside the sequences"; return 1; }
+	CU(h, cudaSetDevice(h->cfg.device));
+	auto& d = h->dg;
+	d.part = *p; d.B = grid_width; d.bh = block_height;
+	d.split.assign(split, split + grid_width + 1);
+	for (int b = 0; b < grid_width; b++)
+		if (d.split[b + 1] <= d.split[b] || d.split[b] < p->j0 || d.split[b + 1] > p->j1) { h->err = "b200_diag_begin: bad column split"; return 1; }
+	const size_t slot = (size_t)block_height + 1;
+	CU(h, d.vbuf.reserve(2 * (size_t)(grid_width + 1) * slot));
+	CU(h, d.col0.reserve(2 * slot));
+	CU(h, h->jobs.reserve(grid_width));
+	CU(h, h->progress.reserve(grid_width));
+	CU(h, h->results.reserve(grid_width));
+	CU(h, h->hresults.reserve(grid_width));
+	CU(h, h->hcells.reserve(std::max<size_t>((size_t)(p->j1 - p->j0) + 1, slot + 1)));
+	CU(h, h->scalars.reserve(8));
+	CU(h, h->hscalars.reserve(8));
+	d.col0_cur = 0; d.col0_valid[0] = d.col0_valid[1] = false;
+	d.last_diag = -1;
+	b200_score z; z.score = -kInf; z.i = -1; z.j = -1;
+	d.scores.assign(grid_width, z);
+	d.active = true;
+	return 0;
+}
+
+extern "C" int b200_diag_set_first_row(b200_handle* h, const b200_cell* cells, int j, int len) {
+	if (!h || !h->dg.active) return 1;
+	if (!cells || j < 0 || len < 0 || j + len > h->n1) { h->err = "b200_diag_set_first_row: bad range"; return 1; }
+	CU(h, cudaMemcpyAsync(h->busH.p + j, cells, (size_t)len * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+extern "C" int b200_diag_set_first_column(b200_handle* h, const b200_cell* cells, int i, int len) {
+	if (!h || !h->dg.active) return 1;
+	auto& d = h->dg;
+	(void)i; (void)len;
+	// cells[0] = diagonal cell, cells[1..bh] = (H,E) of the chunk; consumed by block (0, by) one call later
+	const size_t slot = (size_t)d.bh + 1;
+	int nxt = d.col0_cur ^ 1;
+	CU(h, cudaMemcpyAsync(d.col0.p + nxt * slot, cells, slot * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
+	d.col0_valid[nxt] = true;
+	return 0;
+}
+
+extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, int window_right) {
+	if (!h || !h->dg.active) return 1;
+	CU(h, cudaSetDevice(h->cfg.device));
+	auto& d = h->dg;
+	const b200_partition& p = d.part;
+	const size_t slot = (size_t)d.bh + 1;
+	const int kind = pick_kernel(h, 0);
+	const int SH = strip_height(kind);
+	if (d.bh > SH) { h->err = "b200_diag_process: block height larger than a strip"; return 1; }
+	const int par = diagonal & 1;
+	// Lay the left/right border regions out in one address space: [0, 2*(B+1)*slot) = vbuf, then col0.
+	// StripParams::left and ::right both point at vbuf; col0 is addressed through a second launch-free trick:
+	// block 0 reads its border from col0 copied into vbuf slot [par][0] below.
+	if (p.first_col_init != B200_INIT_ZEROES && d.col0_valid[d.col0_cur]) {
+		CU(h, cudaMemcpyAsync(d.vbuf.p + ((size_t)par * (d.B + 1) + 0) * slot, d.col0.p + d.col0_cur * slot, slot * sizeof(Cell), cudaMemcpyDeviceToDevice, h->stream));
+	}
+	h->hjobs.clear();
+	std::vector<int> job_bx;
+	for (int bx = d.B - 1; bx >= 0; bx--) {
+		int by = diagonal - 1 - bx;
+		d.scores[bx].score = -kInf; d.scores[bx].i = d.scores[bx].j = -1;
+		if (by < 0) continue;
+		long long i0 = (long long)p.i0 + (long long)by * d.bh;
+		if (i0 >= p.i1) continue;
+		int i1 = (int)std::min<long long>(i0 + d.bh, p.i1);
+		StripJob j;
+		memset(&j, 0, sizeof(j));
+		j.i0 = (int)i0; j.rows = i1 - (int)i0; j.j0 = d.split[bx]; j.cols = d.split[bx + 1] - d.split[bx];
+		j.dep = -1;
+		j.flags = 0;
+		if (bx == 0 && p.first_col_init == B200_INIT_ZEROES) j.flags |= JOB_LEFT_ZERO;
+		if (bx < window_left || bx > window_right) j.flags |= JOB_PRUNED;
+		j.left_off = (int)(((size_t)par * (d.B + 1) + bx) * slot);
+		j.right_off = (int)(((size_t)(par ^ 1) * (d.B + 1) + bx + 1) * slot);
+		j.sra_off = -1;
+		h->hjobs.push_back(j);
+		job_bx.push_back(bx);
+	}
+	d.col0_cur ^= 1;                      // col0cur = col0next (oracle_cpu.cpp / CUDAligner.cpp:474-504)
+	d.last_diag = diagonal;
+	const int njobs = (int)h->hjobs.size();
+	if (njobs == 0) return 0;
+	if (reset_scalars(h, -kInf)) return 1;
+	CU(h, cudaMemcpyAsync(h->jobs.p, h->hjobs.data(), njobs * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
+	Cell* save_left = h->left.p; Cell* save_right = h->right.p;
+	h->left.p = d.vbuf.p; h->right.p = d.vbuf.p;
+	int rc = launch_strips(h, njobs, p.recurrence, 1, kind);
+	h->left.p = save_left; h->right.p = save_right;
+	if (rc) return 1;
+	CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
+	CU(h, cudaGetLastError());
+	for (int k = 0; k < njobs; k++) {
+		const Score3& s = h->hresults.p[k];
+		b200_score& o = d.scores[job_bx[k]];
+		o.score = s.score; o.i = s.i; o.j = s.j;
+	}
+	h->stat_cells += (long long)*reinterpret_cast<unsigned long long*>(h->hscalars.p + 4);
+	return 0;
+}
+
+extern "C" int b200_diag_get_row(b200_handle* h, int j, int len, b200_cell* out) {
+	if (!h || !h->dg.active) return 1;
+	if (!out || j < 0 || len < 0 || j + len > h->n1) { h->err = "b200_diag_get_row: bad range"; return 1; }
+	CU(h, cudaMemcpyAsync(out, h->busH.p + j, (size_t)len * sizeof(Cell), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+extern "C" int b200_diag_get_last_column(b200_handle* h, int i, int len, b200_cell* out) {
+	if (!h || !h->dg.active) return 1;
+	auto& d = h->dg;
+	(void)i;
+	if (!out || len < 0 || len > d.bh) { h->err = "b200_diag_get_last_column: bad range"; return 1; }
+	// the last block column wrote its right border for the diagonal just processed into parity (last_diag+1)&1, slot B
+	const size_t slot = (size_t)d.bh + 1;
+	const int par = (d.last_diag + 1) & 1;
+	CU(h, cudaMemcpyAsync(out, d.vbuf.p + ((size_t)par * (d.B + 1) + d.B) * slot + 1, (size_t)len * sizeof(Cell), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
+	return 0;
+}
+
+extern "C" int b200_diag_get_block_scores(b200_handle* h, b200_score* out) {
+	if (!h || !h->dg.active || !out) return 1;
+	memcpy(out, h->dg.scores.data(), h->dg.scores.size() * sizeof(b200_score));
+	return 0;
+}
+
+extern "C" int b200_diag_clear_pruned(b200_handle* h, int j0, int j1) {
+	if (!h || !h->dg.active) return 1;
+	if (j0 < 0 || j1 > h->n1) { h->err = "b200_diag_clear_pruned: bad range"; return 1; }
+	if (j1 <= j0) return 0;
+	long long n = (long long)j1 - j0;
+	fill_const_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->busH.p + j0, n, -kInf, -kInf);
+	h->stat_launches++;
+	CU(h, cudaGetLastError());
+	return 0;
+}
+
+extern "C" int b200_diag_end(b200_handle* h) {
+	if (!h) return 1;
+	h->dg.active = false;
+	return 0;
+}
+
+extern "C" int b200_match_last_column(b200_handle* h, const b200_cell* buffer, const b200_cell* base, int len, int goal, b200_match* out) {
+	if (!h) return 1;
+	if (!buffer || !base || !out || len < 0) { h->err = "b200_match_last_column: bad arguments"; return 1; }
+	out->found = 0; out->k = -1; out->score = 0; out->type = 0;
+	if (len == 0) return 0;
+	CU(h, cudaSetDevice(h->cfg.device));
+	CU(h, h->left.reserve(2 * (size_t)len + 2));
+	CU(h, h->scalars.reserve(8));
+	CU(h, h->hscalars.reserve(8));
+	Cell* dbuf = h->left.p; Cell* dbase = h->left.p + len;
+	CU(h, cudaMemcpyAsync(dbuf, buffer, (size_t)len * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaMemcpyAsync(dbase, base, (size_t)len * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+	h->hscalars.p[0] = INT_MAX;
+	CU(h, cudaMemcpyAsync(h->scalars.p + 3, h->hscalars.p, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	match_column_kernel<<<(len + 255) / 256, 256, 0, h->stream>>>(dbuf, dbase, len, goal, kGapOpen, h->scalars.p + 3);
+	h->stat_launches++;
+	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaStreamSynchronize(h->stream));
+	int code = h->hscalars.p[0];
+	if (code != INT_MAX) {
+		int k = code >> 2, kindc = code & 3;
+		out->k = k;
+		if (kindc == 0) { out->found = 1; out->score = base[k].h; out->type = 0; }
+		else if (kindc == 1) { out->found = 1; out->score = base[k].x; out->type = 1; }
+		else { out->found = 0; out->type = kindc == 2 ? -1 : -2; }
+	}
+	return 0;
+}

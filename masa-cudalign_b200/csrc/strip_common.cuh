@@ -1,0 +1,93 @@
+// strip_common.cuh -- shared definitions of the strip ("chained wavefront") kernels.
+//
+// Work decomposition (B200-first; replaces the grid/external-diagonal scheme of R/src/CUDAligner.cu:745-1156):
+//   * the partition is cut into horizontal STRIPS of at most SH rows; one WARP owns one strip at a time and
+//     sweeps it left to right, lanes skewed by one column (anti-diagonal wavefront inside the warp);
+//   * every lane keeps R rows of the strip in registers; neighbouring lanes exchange the (H,F) border with
+//     warp shuffles; no shared-memory traffic or barrier in the cell loop;
+//   * the strip's bottom row goes to the horizontal bus busH (int32 (H,F) per column, L2 resident) in
+//     coalesced 32-column bursts, followed by a release-store of the strip's progress counter; the warp of
+//     the strip below spins on that counter (acquire) before it loads the same 32 columns as its top border:
+//     strips are chained through L2, never through the host;
+//   * strips are claimed from an atomic counter in row order, so a waiting warp always waits on a strip that
+//     is owned by a resident, running warp: no deadlock as long as the grid fits on the GPU (the launcher
+//     sizes it from the occupancy API).
+// The same kernels run the "diag" compatibility path: there a job is one block of the reference's grid and
+// jobs of one launch do not depend on each other.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200 {
+
+constexpr int kInf = 999999999;                // C/libmasa/libmasaTypes.hpp:46
+constexpr int kMatch = 1, kMismatch = -3;      // R/src/CUDAligner.hpp:77-98
+constexpr int kGapOpen = 3, kGapExt = 2, kGapFirst = kGapOpen + kGapExt;
+
+struct Cell { int h; int x; };                 // == cell_t (x = F in rows, E in columns)
+struct Score3 { int score; int i; int j; int pad; };
+
+enum JobFlags : int {
+	JOB_LEFT_ZERO = 1,      // left border is the constant (H=0, E=-INF): SW stage 1 first column
+	JOB_PRUNED    = 2,      // do not compute: write -INF to the right border (CUDAligner.cu:950-960 semantics)
+	JOB_TOP_MINF  = 4,      // treat the top border as -INF instead of reading busH (strip above was pruned)
+};
+
+struct StripJob {
+	int i0, rows;           // first row (index into seq0) and number of rows (1..SH)
+	int j0, cols;           // first column (index into seq1) and number of columns (>= 1)
+	int dep;                // job whose progress gates our top border, or -1
+	int flags;              // JobFlags
+	int left_off;           // cell index of slot 0 (corner) of our left border in StripParams::left; slots 1..rows follow
+	int right_off;          // cell index of slot 0 of our right border in StripParams::right, or -1
+	long long sra_off;      // cell index in StripParams::sra where column j0 of our bottom row goes, or -1
+	long long pad;
+};
+
+struct StripParams {
+	const unsigned char* s0;
+	const unsigned char* s1;
+	Cell* busH;             // [seq1_len] (H,F) of the row above the strip being read / bottom row being written
+	const Cell* left;       // left borders  (H,E)
+	Cell* right;            // right borders (H,E)
+	Cell* sra;              // on-device special-rows area
+	const StripJob* jobs;
+	int njobs;
+	int* job_counter;       // atomic claim counter (zeroed before launch)
+	int* progress;          // [njobs] columns of the bottom row published so far
+	Score3* results;        // [njobs] best cell of each job (track != 0)
+	int* global_best;       // running best score of the whole partition (atomicMax)
+	unsigned long long* cells_done;   // statistics
+	const int* stop_flag;   // host-mapped: non-zero asks the kernel to stop claiming jobs
+	int recurrence;         // B200_SMITH_WATERMAN | B200_NEEDLEMAN_WUNSCH
+	int track;              // 0: no best tracking; 1: exact best cell per job; 2: per job, thresholded by global_best
+};
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+	int v;
+	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+	int v;
+	asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ Cell ldcg_cell(const Cell* p) {
+	int2 v = __ldcg(reinterpret_cast<const int2*>(p));
+	Cell c; c.h = v.x; c.x = v.y; return c;
+}
+__device__ __forceinline__ void stcg_cell(Cell* p, int h, int x) {
+	__stcg(reinterpret_cast<int2*>(p), make_int2(h, x));
+}
+
+// lexicographic "better" for best cells: higher score, then smaller i, then smaller j
+// (CPUBlockProcessor.cpp:154-158 row-major strict '<' + BestScoreList.hpp:30-38)
+__device__ __forceinline__ bool better(int s, int i, int j, int bs, int bi, int bj) {
+	return s > bs || (s == bs && (i < bi || (i == bi && j < bj)));
+}
+
+}  // namespace b200

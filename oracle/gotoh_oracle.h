@@ -1,0 +1,38 @@
+/* oracle/gotoh_oracle.h -- TEST INFRASTRUCTURE ONLY (see gotoh_oracle.c). */
+#ifndef GOTOH_ORACLE_H
+#define GOTOH_ORACLE_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct { int h; int x; } go_cell;          /* x = F for row cells, E for column cells (libmasaTypes.hpp:35-41) */
+typedef struct { int score, i, j; } go_score;      /* 0-based cell indices (libmasaTypes.hpp:88-95) */
+typedef struct { int found, k, score, type; } go_match;   /* libmasaTypes.hpp:51-60 */
+typedef struct { int type, i, j, score; } go_xpoint;      /* common/Crosspoint.hpp */
+
+#define GO_INF 999999999
+#define GO_SW 1   /* SMITH_WATERMAN  (libmasa/IManager.hpp) */
+#define GO_NW 2   /* NEEDLEMAN_WUNSCH */
+
+/* init types (common/io/InitialCellsReader.cpp:84-108) */
+#define GO_INIT_ZEROES 0
+#define GO_INIT_GAPS 1          /* h = -ext*pos - open  */
+#define GO_INIT_GAPS_OPENED 2   /* h = -ext*pos         */
+#define GO_INIT_CUSTOM 3
+
+int go_full_matrix(const unsigned char* s0, int m, const unsigned char* s1, int n, int recurrence,
+                   const go_cell* first_row /*n+1 or NULL*/, int first_row_type,
+                   const go_cell* first_col /*m+1 or NULL*/, int first_col_type,
+                   const int* row_ids, int n_rows, go_cell* rows_out /* n_rows*(n+1) */,
+                   go_cell* last_col_out /* m+1 or NULL */, go_score* best_out);
+
+void go_init_cells(go_cell* buf, int len, int type, int start_pos);
+
+go_match go_match_column(const go_cell* buffer, const go_cell* base, int len, int goal, int gap_open);
+
+int go_block_prunable(int score, int best, int i0, int j0, int i1, int j1, int max_i, int max_j, int recurrence);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,103 @@
+"""ctypes access to the plain-C oracle (oracle/_ref/libgotoh_oracle.so) and to the reference-built binaries.
+TEST INFRASTRUCTURE: imported only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+CELL = np.dtype([("h", "<i4"), ("x", "<i4")])
+INF = 999999999
+SW, NW = 1, 2
+INIT_ZEROES, INIT_GAPS, INIT_GAPS_OPENED, INIT_CUSTOM = 0, 1, 2, 3
+
+
+class GoScore(C.Structure):
+    _fields_ = [("score", C.c_int), ("i", C.c_int), ("j", C.c_int)]
+
+
+class GoMatch(C.Structure):
+    _fields_ = [("found", C.c_int), ("k", C.c_int), ("score", C.c_int), ("type", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(REF_DIR, "libgotoh_oracle.so")
+        if not os.path.exists(path):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "port"])
+        _lib = C.CDLL(path)
+        _lib.go_full_matrix.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                        C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.POINTER(GoScore)]
+        _lib.go_init_cells.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.go_init_cells.restype = None
+        _lib.go_match_column.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        _lib.go_match_column.restype = GoMatch
+    return _lib
+
+
+def init_cells(n, kind, start=0):
+    out = np.zeros(n, CELL)
+    lib().go_init_cells(out.ctypes.data, n, kind, start)
+    return out
+
+
+def full_matrix(s0, s1, recurrence=SW, first_row=None, first_row_type=INIT_ZEROES, first_col=None,
+                first_col_type=INIT_ZEROES, row_ids=(), want_last_col=True):
+    """Returns dict(best=(score,i,j), rows={row_id: CELL[n+1]}, last_col=CELL[m+1])."""
+    a = np.ascontiguousarray(s0, dtype=np.uint8)
+    b = np.ascontiguousarray(s1, dtype=np.uint8)
+    m, n = a.size, b.size
+    ids = np.ascontiguousarray(sorted(row_ids), dtype=np.int32)
+    rows = np.zeros((ids.size, n + 1), CELL)
+    last = np.zeros(m + 1, CELL) if want_last_col else None
+    best = GoScore()
+    fr = np.ascontiguousarray(first_row, dtype=CELL) if first_row is not None else None
+    fc = np.ascontiguousarray(first_col, dtype=CELL) if first_col is not None else None
+    rc = lib().go_full_matrix(a.ctypes.data, m, b.ctypes.data, n, recurrence,
+                              fr.ctypes.data if fr is not None else None, first_row_type,
+                              fc.ctypes.data if fc is not None else None, first_col_type,
+                              ids.ctypes.data if ids.size else None, ids.size, rows.ctypes.data if ids.size else None,
+                              last.ctypes.data if last is not None else None, C.byref(best))
+    assert rc == 0
+    return dict(best=(best.score, best.i, best.j), rows={int(i): rows[k] for k, i in enumerate(ids)}, last_col=last)
+
+
+def match_column(buffer, base, goal, gap_open=3):
+    bu = np.ascontiguousarray(buffer, dtype=CELL)
+    ba = np.ascontiguousarray(base, dtype=CELL)
+    r = lib().go_match_column(bu.ctypes.data, ba.ctypes.data, bu.size, goal, gap_open)
+    return dict(found=bool(r.found), k=r.k, score=r.score, type=r.type)
+
+
+def have_ref_binaries():
+    return os.path.exists(os.path.join(REF_DIR, "oracle_cpu")) and os.path.exists(os.path.join(REF_DIR, "oracle_cpu_block"))
+
+
+def run_ref(binary, fasta_a, fasta_b, workdir, extra=(), env=None):
+    """Run oracle/_ref/<binary> (the reference's own CPU path) and return the work directory."""
+    exe = os.path.join(REF_DIR, binary)
+    cmd = [exe, f"--work-dir={workdir}", "--clear", "--verbose=0", *extra, fasta_a, fasta_b]
+    e = dict(os.environ)
+    if env:
+        e.update(env)
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=e)
+    return workdir
+
+
+def read_crosspoints(path):
+    pts = []
+    with open(path) as f:
+        for line in f:
+            line = line.strip()
+            if not line or line in ("START", "END"):
+                continue
+            t, i, j, s = (int(x) for x in line.split(","))
+            pts.append((t, i, j, s))
+    return pts

@@ -1,0 +1,89 @@
+"""GPU parity of the whole-partition path (b200_align_partition) against the plain-C oracle.
+Bit-exact: best score + coordinates, special rows, last row, last column."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(m, n, seed, frac=0.6):
+    a0 = int(m * 0.2)
+    a1 = int(m * (0.2 + frac))
+    return synth.make_pair(m, n, [(a0, a1)], 0.05, 0.01, 0.01, 0, seed)
+
+
+@pytest.mark.parametrize("kernel", ["s32", "s16x2"])
+@pytest.mark.parametrize("m,n,seed", [(700, 900, 1), (1, 1, 2), (33, 5, 3), (512, 512, 4), (513, 31, 5), (2049, 1500, 6), (5000, 7000, 7)])
+def test_sw_best_and_borders(b200, kernel, m, n, seed):
+    a, b = _pair(m, n, seed)
+    al = b200.Aligner(kernel=b200.KERNEL_S32 if kernel == "s32" else b200.KERNEL_S16X2)
+    al.set_sequences(a, b)
+    r = al.align_partition(want_last_row=True, want_last_column=True)
+    o = O.full_matrix(a, b, O.SW, row_ids=[m - 1])
+    assert r["best"] == o["best"]
+    assert r["cells"] == m * n
+    lr = r["rows"][m]
+    assert np.array_equal(lr, o["rows"][m - 1])
+    assert np.array_equal(r["last_column"], o["last_col"])
+    al.close()
+
+
+@pytest.mark.parametrize("kernel", ["s32", "s16x2"])
+@pytest.mark.parametrize("m,n", [(9000, 3000), (20000, 1111)])
+def test_special_rows(b200, kernel, m, n):
+    a, b = _pair(m, n, 11)
+    al = b200.Aligner(kernel=b200.KERNEL_S32 if kernel == "s32" else b200.KERNEL_S16X2)
+    al.set_sequences(a, b)
+    r = al.align_partition(want_special_rows=True, special_row_interval=1000, want_last_row=True)
+    ids = sorted(i for i in r["rows"] if i != m)
+    assert ids == list(range(8192, m, 8192))           # 8192-row floor of AbstractDiagonalAligner.cpp:35,466-478
+    o = O.full_matrix(a, b, O.SW, row_ids=[i - 1 for i in ids] + [m - 1])
+    for i in ids + [m]:
+        assert np.array_equal(r["rows"][i], o["rows"][i - 1]), f"special row {i}"
+    assert r["best"] == o["best"]
+    al.close()
+
+
+@pytest.mark.parametrize("kernel", ["s32", "s16x2"])
+@pytest.mark.parametrize("rt,ct", [(O.INIT_GAPS, O.INIT_GAPS), (O.INIT_GAPS_OPENED, O.INIT_GAPS), (O.INIT_GAPS, O.INIT_ZEROES)])
+def test_nw_global(b200, kernel, rt, ct):
+    m, n = 3001, 2500
+    a, b = _pair(m, n, 21, frac=0.75)
+    al = b200.Aligner(kernel=b200.KERNEL_S32 if kernel == "s32" else b200.KERNEL_S16X2)
+    al.set_sequences(a, b)
+    r = al.align_partition(recurrence=b200.NEEDLEMAN_WUNSCH, first_row_init=rt, first_col_init=ct,
+                           want_last_row=True, want_last_column=True, want_best_score=False)
+    o = O.full_matrix(a, b, O.NW, first_row_type=rt, first_col_type=ct, row_ids=[m - 1])
+    assert np.array_equal(r["rows"][m], o["rows"][m - 1])
+    assert np.array_equal(r["last_column"], o["last_col"])
+    al.close()
+
+
+def test_custom_borders_subpartition(b200):
+    """A partition in the middle of the sequences with caller-supplied first row / column (stage 2/3 shape)."""
+    a, b = _pair(4000, 4000, 31)
+    i0, j0, i1, j1 = 700, 300, 3100, 3333
+    rng = np.random.default_rng(5)
+    fr = np.zeros(j1 - j0 + 1, O.CELL); fc = np.zeros(i1 - i0 + 1, O.CELL)
+    fr["h"] = -np.cumsum(rng.integers(0, 4, fr.size)); fr["x"] = fr["h"] - rng.integers(1, 9, fr.size)
+    fc["h"] = -np.cumsum(rng.integers(0, 4, fc.size)); fc["x"] = fc["h"] - rng.integers(1, 9, fc.size)
+    fc[0] = fr[0]
+    for kernel in (b200.KERNEL_S32, b200.KERNEL_S16X2):
+        al = b200.Aligner(kernel=kernel)
+        al.set_sequences(a, b)
+        r = al.align_partition(i0, j0, i1, j1, recurrence=b200.NEEDLEMAN_WUNSCH, first_row_init=b200.INIT_CUSTOM,
+                               first_col_init=b200.INIT_CUSTOM, first_row=fr, first_col=fc, want_last_row=True,
+                               want_last_column=True, want_best_score=True)
+        o = O.full_matrix(a[i0:i1], b[j0:j1], O.NW, first_row=fr, first_col=fc, row_ids=[i1 - i0 - 1])
+        assert np.array_equal(r["rows"][i1][1:], o["rows"][i1 - i0 - 1][1:])
+        assert np.array_equal(r["last_column"][1:], o["last_col"][1:])
+        assert r["best"] == (o["best"][0], o["best"][1] + i0, o["best"][2] + j0)
+        al.close()
