@@ -146,21 +146,35 @@ __global__ void match_column_kernel(const Cell* buffer, const Cell* base, int le
 	if ((threadIdx.x & 31) == 0 && code != INT_MAX) atomicMin(out, code);
 }
 
-int grid_for(b200_handle* h, const void* kernel, int njobs) {
+// Grid of the persistent strip kernel.  All CTAs must be co-resident (a strip spins on the progress of the
+// strip above it), so the grid never exceeds SMs x occupancy.  Below that limit the number of resident warps
+// per SM is chosen so that the strips fill whole waves: every strip sweeps the full width at the pace of one
+// warp, so a last, nearly empty wave would cost as much as a full one.  kSatWarps is the measured number of
+// strip-warps that saturate an SM's VIADDMNMX pipe (profiles/r01_*): more warps only stretch each wave.
+constexpr int kSatWarps = 7;
+int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 	int per_sm = 0;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, 0);
 	if (per_sm < 1) per_sm = 1;
-	if (h->cfg.warps_per_sm > 0) {
-		int lim = (h->cfg.warps_per_sm + kWarpsPerBlock - 1) / kWarpsPerBlock;
-		if (lim < per_sm) per_sm = lim;
+	int lim = per_sm * kWarpsPerBlock;
+	if (h->cfg.warps_per_sm > 0) lim = std::min(lim, h->cfg.warps_per_sm);
+	int best_w = lim;
+	if (h->cfg.warps_per_sm <= 0 && chained && njobs > h->sm_count * kSatWarps) {
+		double best_cost = 1e300;
+		for (int w = std::min(kSatWarps, lim); w <= lim; w++) {
+			long long cap = (long long)h->sm_count * w;
+			long long waves = (njobs + cap - 1) / cap;
+			double cost = (double)waves * std::max(kSatWarps, w);
+			if (cost < best_cost - 1e-9) { best_cost = cost; best_w = w; }
+		}
 	}
-	int cap = per_sm * h->sm_count;                      // co-residency bound: required by the flag-chained strips
+	int cap = best_w * h->sm_count / kWarpsPerBlock;
 	int need = (njobs + kWarpsPerBlock - 1) / kWarpsPerBlock;
 	return std::max(1, std::min(cap, need));
 }
 
 // Launch the strip kernel over h->hjobs (already uploaded to h->jobs).
-int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kernel_kind) {
+int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kernel_kind, int SH, bool chained) {
 	StripParams sp;
 	sp.s0 = h->s0.p; sp.s1 = h->s1.p;
 	sp.busH = h->busH.p; sp.left = h->left.p; sp.right = h->right.p; sp.sra = h->sra.p;
@@ -175,14 +189,17 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.track = track;
 	const bool sw = recurrence == B200_SMITH_WATERMAN;
 	const void* fn = nullptr;
-	if (kernel_kind == B200_KERNEL_S16X2) {
+	if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F) {
+		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16F, true, true> : (const void*)strip_kernel_s16<kR16F, true, false>;
+		else    fn = track ? (const void*)strip_kernel_s16<kR16F, false, true> : (const void*)strip_kernel_s16<kR16F, false, false>;
+	} else if (kernel_kind == B200_KERNEL_S16X2) {
 		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16, true, true> : (const void*)strip_kernel_s16<kR16, true, false>;
 		else    fn = track ? (const void*)strip_kernel_s16<kR16, false, true> : (const void*)strip_kernel_s16<kR16, false, false>;
 	} else {
 		if (sw) fn = track ? (const void*)strip_kernel_s32<kR32, true, true> : (const void*)strip_kernel_s32<kR32, true, false>;
 		else    fn = track ? (const void*)strip_kernel_s32<kR32, false, true> : (const void*)strip_kernel_s32<kR32, false, false>;
 	}
-	int grid = grid_for(h, fn, njobs);
+	int grid = grid_for(h, fn, njobs, chained);
 	void* args[] = {(void*)&sp};
 	CU(h, cudaLaunchKernel(fn, dim3(grid), dim3(kWarpsPerBlock * 32), args, 0, h->stream));
 	h->stat_launches++;
@@ -198,15 +215,12 @@ int reset_scalars(b200_handle* h, int global_best) {
 	return 0;
 }
 
-int strip_height(int kernel_kind) { return kernel_kind == B200_KERNEL_S16X2 ? kSH16 : kSH32; }
+int strip_height(int kernel_kind, bool fast) { return kernel_kind == B200_KERNEL_S16X2 ? (fast ? kSH16F : kSH16) : kSH32; }
 
 int pick_kernel(b200_handle* h, int requested) {
 	int k = requested ? requested : h->cfg.kernel;
 	if (k == B200_KERNEL_AUTO) k = h->acgt_only ? B200_KERNEL_S16X2 : B200_KERNEL_S32;
 	if (k == B200_KERNEL_S16X2 && !h->acgt_only) k = B200_KERNEL_S32;   // packed kernel needs 2-bit codes
-#ifdef B200_NO_S16
-	k = B200_KERNEL_S32;
-#endif
 	return k;
 }
 
@@ -325,7 +339,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	if (m <= 0 || n <= 0 || p->i0 < 0 || p->j0 < 0 || p->i1 > h->n0 || p->j1 > h->n1) { h->err = "b200_align_partition: partition outside the sequences"; return 1; }
 	CU(h, cudaSetDevice(h->cfg.device));
 	const int kind = pick_kernel(h, 0);
-	const int SH = strip_height(kind);
+	const int SH = strip_height(kind, true);
 	const bool sw = p->recurrence == B200_SMITH_WATERMAN;
 	const int track = p->want_best_score ? 2 : 0;
 
@@ -406,7 +420,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 
 	// ---- the alignment itself: one persistent launch
 	CU(h, cudaEventRecord(h->ev0, h->stream));
-	if (launch_strips(h, njobs, p->recurrence, track, kind)) return 1;
+	if (launch_strips(h, njobs, p->recurrence, track, kind, SH, true)) return 1;
 	CU(h, cudaEventRecord(h->ev1, h->stream));
 	if (track) CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -537,7 +551,7 @@ extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, 
 	const b200_partition& p = d.part;
 	const size_t slot = (size_t)d.bh + 1;
 	const int kind = pick_kernel(h, 0);
-	const int SH = strip_height(kind);
+	const int SH = strip_height(kind, false);
 	if (d.bh > SH) { h->err = "b200_diag_process: block height larger than a strip"; return 1; }
 	const int par = diagonal & 1;
 	// Lay the left/right border regions out in one address space: [0, 2*(B+1)*slot) = vbuf, then col0.
@@ -576,7 +590,7 @@ extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, 
 	CU(h, cudaMemcpyAsync(h->jobs.p, h->hjobs.data(), njobs * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
 	Cell* save_left = h->left.p; Cell* save_right = h->right.p;
 	h->left.p = d.vbuf.p; h->right.p = d.vbuf.p;
-	int rc = launch_strips(h, njobs, p.recurrence, 1, kind);
+	int rc = launch_strips(h, njobs, p.recurrence, 1, kind, SH, false);
 	h->left.p = save_left; h->right.p = save_right;
 	if (rc) return 1;
 	CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));

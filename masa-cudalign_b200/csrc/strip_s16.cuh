@@ -1,11 +1,394 @@
-// strip_s16.cuh -- placeholder while the packed s16x2 kernel is being brought up: constants only.
+// strip_s16.cuh -- packed s16x2 DPX strip kernel: the production path for A/C/G/T inputs.
+//
+// Two DP cells per 32-bit lane-register.  A warp carries 64 "virtual lanes": virtual lane v = 2*lane + half
+// owns R consecutive rows of the strip and works on column (t - v) at step t, so the low half of a register
+// is always one column ahead of the high half and both halves advance along the same anti-diagonal.  The
+// (H,F) border of virtual lane v-1 reaches v through one warp shuffle plus one PRMT that rotates the halves.
+//
+// Per row PAIR (two cells) the inner loop issues (SW):
+//     PRMT                 substitution scores of both cells: byte-select from the two column profile words
+//     VIADDMNMX.S16x2      E  = max(E - 2, T_left)                    T = H - 5 is the stored form of H
+//     VIADDMNMX.S16x2      x  = max(T_diag + (s+5), zero)             SW clamp folded into the diagonal term
+//     VIADDMNMX.S16x2      F  = max(F - 2, T_up)
+//     VIMNMX3.S16x2        H  = max(x, E, F)
+//     VIADD.16x2           T  = H - 5                                 (issues down the other integer pipe)
+//     VIMNMX.S16x2         running maximum for best-score tracking
+// i.e. ~3.5 ALU-pipe slots per cell against ~7-8 for the int32 kernel (PRMT counts double: measured 32 vs
+// 64 lanes/clk/SM, profiles/r01_pipe_rates.txt).
+//
+// Range: scores are kept relative to a per-warp base that is re-centred every 32 columns when the reference
+// cell drifts by more than kRebase, so all live values stay inside s16.  Neighbouring DP cells differ by a
+// bounded amount, so the spread over a warp's parallelogram (64*R rows x 64 columns) is < 13k for R <= 32.
+// -INF border inputs (E/F of first row/column, pruned neighbours in SW) are clamped to kNeg and vanish after
+// one cell exactly as -INF does in the reference; NW partitions whose H inputs are -INF take the int32 kernel.
+// Results (bottom row, right column, best cell) are converted back to the reference's exact int32 values.
 #pragma once
 #include "strip_common.cuh"
 #include "strip_s32.cuh"
+
 namespace b200 {
-constexpr int kR16 = 8;
+
+constexpr int kR16 = 8;                 // diag-compat instance: 64*8  = 512-row strips (reference block height)
 constexpr int kSH16 = 64 * kR16;
-#define B200_NO_S16 1
+constexpr int kR16F = 16;               // whole-partition instance: 64*16 = 1024-row strips
+constexpr int kSH16F = 64 * kR16F;
+
+constexpr int kNeg = -30000;            // local-frame stand-in for -INF
+constexpr int kRebase = 4096;           // re-centre when |reference cell| exceeds this
+constexpr int kCand = 32;               // candidate-ring entries per warp (>= 32: one step can trigger every lane)
+
+__device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
+__device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
+__device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
+__device__ __forceinline__ int clamp16(int v) { return v < kNeg ? kNeg : (v > 32767 ? 32767 : v); }
+__device__ __forceinline__ unsigned dup2(int v) { return pack2(v, v); }
+// raw PRMT: unlike __byte_perm (which masks the selector with 0x7777) bit 3 of a selector nibble replicates the
+// sign bit of the selected byte, which is how one instruction yields two sign-extended s16 scores
+__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
+	unsigned d;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+	return d;
+}
+__device__ __forceinline__ unsigned thr_pack(int thr, int base) {
+	if (thr == INT_MIN) return 0x80008000u;
+	const long long d = (long long)thr - base;
+	const int v = d > 32767 ? 32767 : (d < -32768 ? -32768 : (int)d);
+	return ((unsigned)v & 0xffffu) | ((unsigned)v << 16);
+}
+__device__ __forceinline__ int code_of(int c) { return (c >> 1) & 3; }     // A->0 C->1 T->2 G->3
+
 template <int R, bool SW, bool TRACK>
-__global__ void strip_kernel_s16(const StripParams p) {}
+struct StripS16 {
+	static constexpr int V = 64;
+	static constexpr int SH = V * R;
+
+	struct Smem {
+		int2 top[kWarpsPerBlock][32];        // {H<<16, F<<16} of the top border in the local frame
+		unsigned prof[kWarpsPerBlock][32];   // column profile words: byte k = s(k, column base) + 5
+		int2 bot[kWarpsPerBlock][64];        // local (H,F) of the strip's bottom row, ring over columns
+		unsigned cand[kWarpsPerBlock][kCand][R + 2];   // deferred best-cell candidates: T[0..R) of a lane + {step, lane|halves<<8}
+	};
+
+	// all per-warp state of one job
+	struct State {
+		unsigned T[R], E[R], sel[R];
+		unsigned tprev, botH, botF, pa, pb;
+		unsigned Zp, thrp;
+		int base;
+		int bs, bi, bj, thr, pub, ncand;
+	};
+
+	template <bool PARTIAL, bool CHECK>
+	__device__ __forceinline__ static void step(const StripParams& p, const StripJob& jb, State& s, Smem& sm, int warp, int lane,
+	                                            int t, int u, int nv_lo, int nv_hi, int vo, int ro) {
+		const unsigned M2 = dup2(-kGapExt), M5 = dup2(-kGapFirst);
+		unsigned shH = __shfl_up_sync(0xffffffffu, s.botH, 1);
+		unsigned shF = __shfl_up_sync(0xffffffffu, s.botF, 1);
+		unsigned shP = __shfl_up_sync(0xffffffffu, s.pb, 1);
+		const int2 tv = sm.top[warp][u];
+		const unsigned tp = sm.prof[warp][u];
+		if (lane == 0) { shH = (unsigned)tv.x; shF = (unsigned)tv.y; shP = tp; }
+		const unsigned upH = prmt(shH, s.botH, 0x5432);      // lo <- neighbour's hi, hi <- own lo
+		const unsigned upF = prmt(shF, s.botF, 0x5432);
+		s.pb = s.pa; s.pa = shP;
+		const int col_lo = t - 2 * lane, col_hi = col_lo - 1;
+		bool act = true;
+		if (CHECK) act = (col_lo >= 0) && (col_hi < jb.cols);       // at least one half inside the strip
+		bool trig = false, trig_lo = false, trig_hi = false;
+		if (act) {
+			unsigned dT = s.tprev;
+			unsigned tup = __vadd2(upH, M5);
+			unsigned f = upF, h = 0, smax = dup2(-32768), oh = 0, of = 0;
+			// during fill/drain one half may be outside [0, cols): its state must not move
+			unsigned keep = 0;                                        // halves to freeze: 0xffff lo, 0xffff0000 hi
+			if (CHECK) {
+				if (col_lo >= jb.cols) keep |= 0x0000ffffu;
+				if (col_hi < 0) keep |= 0xffff0000u;
+			}
+			s.tprev = CHECK ? ((tup & ~keep) | (s.tprev & keep)) : tup;
+#pragma unroll
+			for (int r = 0; r < R; r++) {
+				const unsigned sc = prmt(s.pa, s.pb, s.sel[r]);
+				const unsigned e = __viaddmax_s16x2(s.E[r], M2, s.T[r]);
+				const unsigned x = SW ? __viaddmax_s16x2(dT, sc, s.Zp) : __vadd2(dT, sc);
+				f = __viaddmax_s16x2(f, M2, tup);
+				h = __vimax3_s16x2(x, e, f);
+				dT = s.T[r];
+				tup = __vadd2(h, M5);
+				if (CHECK) { s.E[r] = (e & ~keep) | (s.E[r] & keep); s.T[r] = (tup & ~keep) | (s.T[r] & keep); }
+				else { s.E[r] = e; s.T[r] = tup; }
+				if (TRACK) smax = __vmaxs2(smax, h);
+				if (PARTIAL && r == ro) { oh = h; of = f; }
+			}
+			if (!PARTIAL) { oh = h; of = f; }
+			if (CHECK) { s.botH = (h & ~keep) | (s.botH & keep); s.botF = (f & ~keep) | (s.botF & keep); }
+			else { s.botH = h; s.botF = f; }
+
+			if (lane == (vo >> 1)) {
+				const int oc = (vo & 1) ? col_hi : col_lo;
+				if (!CHECK || (unsigned)oc < (unsigned)jb.cols) {
+					int2 o;
+					o.x = (vo & 1) ? hi16(oh) : lo16(oh);
+					o.y = (vo & 1) ? hi16(of) : lo16(of);
+					sm.bot[warp][oc & 63] = o;
+				}
+			}
+			if (TRACK) {
+				bool plo, phi;
+				(void)__vibmax_s16x2(smax, s.thrp, &phi, &plo);
+				trig_lo = plo; trig_hi = phi; trig = phi || plo;
+			}
+			if (CHECK && jb.right_off >= 0) {
+				Cell* rb = p.right + jb.right_off;
+				if (col_lo == jb.cols - 1) {
+#pragma unroll
+					for (int r = 0; r < R; r++)
+						if (r < nv_lo) stcg_cell(rb + 1 + (2 * lane) * R + r, lo16(s.T[r]) + kGapFirst + s.base, lo16(s.E[r]) + s.base);
+					if (lane == 0) { const int cv = hi16(shH); __stcg(&rb[0].h, cv <= kNeg ? -kInf : cv + s.base); }   // corner for the block on our right
+				}
+				if (col_hi == jb.cols - 1) {
+#pragma unroll
+					for (int r = 0; r < R; r++)
+						if (r < nv_hi) stcg_cell(rb + 1 + (2 * lane + 1) * R + r, hi16(s.T[r]) + kGapFirst + s.base, hi16(s.E[r]) + s.base);
+				}
+			}
+		}
+		if (TRACK) {
+			// Rare path, deferred: a lane whose column pair ties/beats the best known so far parks its R packed
+			// H registers in the warp's candidate ring (a handful of STS); the exact (score,i,j) bookkeeping is done
+			// by all 32 lanes together in drain(), every 32 columns, so the strip that carries the alignment path
+			// does not throttle the strips chained below it.
+			const unsigned mask = __ballot_sync(0xffffffffu, trig);
+			if (mask) {
+				const int n = __popc(mask);
+				if (s.ncand + n > kCand) drain(jb, s, sm, warp, lane);
+				if (trig) {
+					const int slot = s.ncand + __popc(mask & ((1u << lane) - 1u));
+					unsigned* e = sm.cand[warp][slot];
+#pragma unroll
+					for (int r = 0; r < R; r++) e[r] = s.T[r];
+					e[R] = (unsigned)t;
+					e[R + 1] = (unsigned)lane | (trig_lo ? 0x100u : 0u) | (trig_hi ? 0x200u : 0u);
+				}
+				s.ncand += n;
+			}
+		}
+	}
+
+	struct Best { int bs, bi, bj; };
+
+	// Cooperative scan of the candidate ring: lane l examines cell (half = l / R, row = l % R) of every entry.
+	// Takes and returns scalars only, so the register-resident State never has its address taken.
+	__device__ __noinline__ static Best drain_scan(const unsigned (*cand)[R + 2], int ncand, int rows, int cols, int i0, int j0,
+	                                               int base, int lane, Best b) {
+		__syncwarp();
+		const int half = lane / R, r = lane % R;
+		for (int e = 0; e < ncand; e++) {
+			const unsigned* en = cand[e];
+			const unsigned meta = en[R + 1];
+			const int te = (int)en[R], src = (int)(meta & 31u);
+			if (half < 2 && ((meta >> (8 + half)) & 1u)) {
+				const unsigned w = en[r];
+				const int v = 2 * src + half, col = te - v, row = v * R + r;
+				if (row < rows && (unsigned)col < (unsigned)cols) {
+					const int hv = (half ? hi16(w) : lo16(w)) + kGapFirst + base;
+					const int i = i0 + row, j = j0 + col;
+					if (better(hv, i, j, b.bs, b.bi, b.bj)) { b.bs = hv; b.bi = i; b.bj = j; }
+				}
+			}
+		}
+		__syncwarp();
+		return b;
+	}
+
+	__device__ __forceinline__ static void drain(const StripJob& jb, State& s, Smem& sm, int warp, int lane) {
+		Best b; b.bs = s.bs; b.bi = s.bi; b.bj = s.bj;
+		b = drain_scan(sm.cand[warp], s.ncand, jb.rows, jb.cols, jb.i0, jb.j0, s.base, lane, b);
+		s.bs = b.bs; s.bi = b.bi; s.bj = b.bj;
+		s.ncand = 0;
+		const int wb = __reduce_max_sync(0xffffffffu, s.bs);
+		if (wb > s.thr) { s.thr = wb; s.thrp = thr_pack(s.thr, s.base); }
+	}
+
+	template <bool PARTIAL>
+	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane) {
+		const StripJob jb = p.jobs[job];
+		const int rows = jb.rows, cols = jb.cols, i0 = jb.i0, j0 = jb.j0;
+		const int rb_lo = (2 * lane) * R, rb_hi = (2 * lane + 1) * R;     // first row of each half inside the strip
+		int nv_lo = rows - rb_lo; nv_lo = nv_lo < 0 ? 0 : (nv_lo > R ? R : nv_lo);
+		int nv_hi = rows - rb_hi; nv_hi = nv_hi < 0 ? 0 : (nv_hi > R ? R : nv_hi);
+		const int vo = (rows - 1) / R, ro = (rows - 1) % R;
+
+		State s;
+		// ---- left border; the frame starts at the H of the corner
+		const Cell* lb = p.left + jb.left_off;
+		const bool lz = (jb.flags & JOB_LEFT_ZERO) != 0;
+		int base = 0;
+		if (!lz) {
+			int v0 = 0;
+			if (lane == 0) { v0 = __ldcg(&lb[0].h); if (v0 < -kInf / 2) v0 = __ldcg(&lb[1].h); if (v0 < -kInf / 2) v0 = 0; }
+			base = __shfl_sync(0xffffffffu, v0, 0);
+		}
+		s.base = base;
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			int hl = -kGapFirst - base, el = kNeg, hh = -kGapFirst - base, eh = kNeg, cl = 0, chh = 0;
+			if (r < nv_lo) {
+				cl = code_of(p.s0[i0 + rb_lo + r]);
+				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_lo + r); hl = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); el = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
+			} else { hl = kNeg; }
+			if (r < nv_hi) {
+				chh = code_of(p.s0[i0 + rb_hi + r]);
+				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_hi + r); hh = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); eh = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
+			} else { hh = kNeg; }
+			s.T[r] = pack2(clamp16(hl), clamp16(hh));
+			s.E[r] = pack2(el, eh);
+			s.sel[r] = (unsigned)cl | ((unsigned)(8 | cl) << 4) | ((unsigned)(4 + chh) << 8) | ((unsigned)(12 + chh) << 12);
+		}
+		{
+			// diagonal term of row 0 of each half at its first column: H(row above, column -1) - 5
+			int dl = -kGapFirst - base, dh = -kGapFirst - base;
+			if (!lz) {
+				if (rb_lo < rows) { int v = __ldcg(&lb[rb_lo].h); dl = clamp16(v < -kInf / 2 ? kNeg : v - kGapFirst - base); }
+				if (rb_hi < rows) { int v = __ldcg(&lb[rb_hi].h); dh = clamp16(v < -kInf / 2 ? kNeg : v - kGapFirst - base); }
+			}
+			s.tprev = pack2(dl, dh);
+		}
+		s.botH = 0; s.botF = 0; s.pa = 0x02020202u; s.pb = 0x02020202u;
+		s.Zp = dup2(clamp16(-base));
+		s.bs = INT_MIN; s.bi = -1; s.bj = -1; s.thr = INT_MIN; s.pub = INT_MIN; s.thrp = 0x80008000u; s.ncand = 0;
+
+		int flushed = 0;
+		const int total = cols + V - 1;
+		const bool top_minf = (jb.flags & JOB_TOP_MINF) != 0;
+
+#pragma unroll 1
+		for (int tb = 0; tb < total; tb += 32) {
+			// ---- re-centre the frame on H(row 0 of the strip, last column done by virtual lane 0)
+			if (tb > 0 && tb <= cols) {
+				int ref = lo16(s.T[0]) + kGapFirst;
+				ref = __shfl_sync(0xffffffffu, ref, 0);
+				if (ref > kRebase || ref < -kRebase) {
+					const unsigned d = dup2(-ref), fl = dup2(kNeg + (ref > 0 ? ref : 0));
+#pragma unroll
+					for (int r = 0; r < R; r++) {
+						s.T[r] = __vadd2(__vmaxs2(s.T[r], fl), d);
+						s.E[r] = __vadd2(__vmaxs2(s.E[r], fl), d);
+					}
+					s.tprev = __vadd2(__vmaxs2(s.tprev, fl), d);
+					s.botH = __vadd2(__vmaxs2(s.botH, fl), d);
+					s.botF = __vadd2(__vmaxs2(s.botF, fl), d);
+					s.base += ref;
+					s.Zp = dup2(clamp16(-s.base));
+					s.thrp = thr_pack(s.thr, s.base);
+				}
+			}
+			// ---- stage the next 32 columns of top border and seq1 (coalesced), gated on the strip above
+			if (tb < cols) {
+				const int need = tb + 32 < cols ? tb + 32 : cols;
+				if (jb.dep >= 0) {
+					if (lane == 0) {
+						while (ld_acquire(p.progress + jb.dep) < need) {
+							if (ld_relaxed(p.stop_flag)) break;
+							__nanosleep(64);
+						}
+					}
+					__syncwarp();
+				}
+				const int c = tb + lane;
+				int th = kNeg, tf = kNeg; unsigned pw = 0x02020202u;
+				if (c < cols) {
+					if (!top_minf) {
+						const Cell tv = ldcg_cell(p.busH + j0 + c);
+						th = tv.h < -kInf / 2 ? kNeg : clamp16(tv.h - s.base);
+						tf = tv.x < -kInf / 2 ? kNeg : clamp16(tv.x - s.base);
+					}
+					const int k = code_of(p.s1[j0 + c]);
+					pw = 0x02020202u ^ (0x04u << (8 * k));      // byte k = 6 (match+5), others 2 (mismatch+5)
+				}
+				sm.top[warp][lane] = make_int2((int)((unsigned)th << 16), (int)((unsigned)tf << 16));
+				sm.prof[warp][lane] = pw;
+				if (TRACK && p.track == 2) {
+					// share the running best: publish ours, adopt a higher one (monotone, staleness is harmless)
+					if (s.thr > s.pub) { if (lane == 0) atomicMax(p.global_best, s.thr); s.pub = s.thr; }
+					const int g = ld_relaxed(p.global_best);
+					if (g > s.thr) { s.thr = g; s.pub = g; s.thrp = thr_pack(s.thr, s.base); }
+				}
+				__syncwarp();
+			}
+
+			// ---- 32 steps; the check-free body runs whenever every virtual lane is inside [0, cols)
+			const bool steady = (tb >= V) && (tb + 32 < cols);
+			if (steady) {
+#pragma unroll 1
+				for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro);
+			} else {
+#pragma unroll 1
+				for (int u = 0; u < 32; u++) step<PARTIAL, true>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro);
+			}
+
+			if (TRACK && s.ncand > 0) drain(jb, s, sm, warp, lane);
+
+			// ---- publish the columns of the bottom row completed during these 32 steps (exact int32 values)
+			int cdone = tb + 31 - vo; cdone = cdone < cols - 1 ? cdone : cols - 1;
+			if (cdone >= flushed) {
+				__syncwarp();
+				for (int c = flushed + lane; c <= cdone; c += 32) {
+					const int2 v = sm.bot[warp][c & 63];
+					const int hv = v.x <= kNeg ? -kInf : v.x + s.base, fv = v.y <= kNeg ? -kInf : v.y + s.base;
+					stcg_cell(p.busH + j0 + c, hv, fv);
+					if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, hv, fv);
+				}
+				flushed = cdone + 1;
+				__syncwarp();
+				if (lane == 0) { __threadfence(); st_release(p.progress + job, flushed); }
+			}
+		}
+
+		if (TRACK) {
+			int bs = s.bs, bi = s.bi, bj = s.bj;
+#pragma unroll
+			for (int d = 16; d >= 1; d >>= 1) {
+				const int os = __shfl_xor_sync(0xffffffffu, bs, d);
+				const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+				const int oj = __shfl_xor_sync(0xffffffffu, bj, d);
+				if (better(os, oi, oj, bs, bi, bj)) { bs = os; bi = oi; bj = oj; }
+			}
+			if (lane == 0) {
+				Score3 o; o.score = bs == INT_MIN ? -kInf : bs; o.i = bi; o.j = bj; o.pad = 0;
+				p.results[job] = o;
+				if (bs != INT_MIN) atomicMax(p.global_best, bs);
+			}
+		}
+		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)cols);
+	}
+};
+
+template <int R, bool SW, bool TRACK>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) strip_kernel_s16(const StripParams p) {
+	using K = StripS16<R, SW, TRACK>;
+	__shared__ typename K::Smem sm;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	for (;;) {
+		int job = 0;
+		if (lane == 0) job = atomicAdd(p.job_counter, 1);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= p.njobs) break;
+		if (ld_relaxed(p.stop_flag)) break;
+		const int flags = p.jobs[job].flags, rows = p.jobs[job].rows;
+		if (flags & JOB_PRUNED) {
+			// same semantics as the int32 kernel: -INF to the right border, no score (CUDAligner.cu:950-960)
+			const StripJob jb = p.jobs[job];
+			if (jb.right_off >= 0)
+				for (int k = lane; k <= jb.rows; k += 32) stcg_cell(p.right + jb.right_off + k, -kInf, -kInf);
+			if (TRACK && lane == 0) { Score3 o; o.score = -kInf; o.i = -1; o.j = -1; o.pad = 0; p.results[job] = o; }
+			__syncwarp();
+			if (lane == 0) { __threadfence(); st_release(p.progress + job, jb.cols); }
+			continue;
+		}
+		if (rows < K::SH) K::template run_job<true>(p, job, sm, warp, lane);
+		else K::template run_job<false>(p, job, sm, warp, lane);
+	}
+}
+
 }  // namespace b200

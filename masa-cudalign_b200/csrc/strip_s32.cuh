@@ -13,7 +13,7 @@
 
 namespace b200 {
 
-constexpr int kWarpsPerBlock = 4;
+constexpr int kWarpsPerBlock = 1;   // one strip-warp per CTA: resident warps per SM can be any number up to the register limit
 
 template <int R, bool SW, bool TRACK>
 struct StripS32 {
@@ -65,7 +65,7 @@ struct StripS32 {
 
 		int botH = 0, botF = 0, ccur = 0x200;
 		int bs = INT_MIN, bi = -1, bj = -1;      // exact best candidate of this lane
-		int thr = INT_MIN;                        // enter the rare path when a cell reaches thr
+		int thr = INT_MIN, pub = INT_MIN;         // warp-uniform: enter the rare path when a cell reaches thr
 		int flushed = 0;                          // columns of the bottom row already published
 		const int total = cols + V - 1;
 		const bool top_minf = (jb.flags & JOB_TOP_MINF) != 0;
@@ -92,7 +92,11 @@ struct StripS32 {
 				}
 				sm.top[warp][lane] = tv;
 				sm.seq[warp][lane] = ch;
-				if (TRACK && p.track == 2) { int g = ld_relaxed(p.global_best); thr = thr > g ? thr : g; }
+				if (TRACK && p.track == 2) {
+					if (thr > pub) { if (lane == 0) atomicMax(p.global_best, thr); pub = thr; }
+					const int g = ld_relaxed(p.global_best);
+					if (g > thr) { thr = g; pub = g; }
+				}
 				__syncwarp();
 			}
 
@@ -107,6 +111,7 @@ struct StripS32 {
 				if (lane == 0) { upH = tv.h; upF = tv.x; cc = tc; }
 				ccur = cc;
 				const int col = t - lane;
+				bool trig = false;
 				if ((unsigned)col < (unsigned)cols) {
 					int dT = tprev;
 					int tup = upH - kGapFirst;
@@ -129,8 +134,18 @@ struct StripS32 {
 					if (!partial) { oh = h; of = f; }
 					botH = h; botF = f;
 					if (lane == vo) { Cell o; o.h = oh; o.x = of; sm.bot[warp][col & 63] = o; }
-					if (TRACK && smax >= thr) {
-						// rare path: some cell of this column ties or beats the best known so far
+					if (TRACK) trig = smax >= thr;
+					if (col == cols - 1 && jb.right_off >= 0) {
+						Cell* rb = p.right + jb.right_off;
+#pragma unroll
+						for (int r = 0; r < R; r++)
+							if (r < nvalid) stcg_cell(rb + 1 + row_base + r, T[r] + kGapFirst, E[r]);
+						if (lane == 0) __stcg(&rb[0].h, upH);     // corner for the block on our right
+					}
+				}
+				if (TRACK && __any_sync(0xffffffffu, trig)) {
+					// rare path (warp-uniform): some cell of this anti-diagonal ties or beats the best known so far
+					if (trig) {
 						const int j = j0 + col;
 #pragma unroll
 						for (int r = 0; r < R; r++) {
@@ -139,15 +154,9 @@ struct StripS32 {
 								if (better(hv, i, j, bs, bi, bj)) { bs = hv; bi = i; bj = j; }
 							}
 						}
-						thr = thr > bs ? thr : bs;
 					}
-					if (col == cols - 1 && jb.right_off >= 0) {
-						Cell* rb = p.right + jb.right_off;
-#pragma unroll
-						for (int r = 0; r < R; r++)
-							if (r < nvalid) stcg_cell(rb + 1 + row_base + r, T[r] + kGapFirst, E[r]);
-						if (lane == 0) __stcg(&rb[0].h, upH);     // corner for the block on our right
-					}
+					const int wb = __reduce_max_sync(0xffffffffu, bs);
+					thr = thr > wb ? thr : wb;
 				}
 			}
 
