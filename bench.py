@@ -1,0 +1,361 @@
+#!/usr/bin/env python3
+"""bench.py -- stage-1 Smith-Waterman GCUPS of the B200 strip-wavefront engine (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, through the C ABI)
+  python bench.py --impl reference [--gpus N] ...              the reference's own CPU path (oracle/_ref)
+
+One "step" = one complete stage-1 pass (best score + end coordinate, exact tie-break) over one synthetic pair.
+N = 1: BASELINE config 2 shape, 5 Mbp x 5 Mbp (SURVEY.md 8d cfg2 generator).  N > 1: weak scaling of the
+reference's own multi-GPU scheme (column slices, chained wavefront): rows grow with N (m = 5M*N, n = 5M), every
+GPU owns n/N columns of all rows, the slice-border column streams to the next GPU through peer memory from
+inside the strip kernel (no collective on the data path).  value = m*n*K / (max over ranks of the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+METRIC = "GCUPS (stage-1 SW, device-timed)"
+BASE_M = 5_000_000
+BASE_N = 5_000_000
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_workload(n_gpus, scale=1.0):
+    import synth
+    c = dict(synth.CONFIGS["cfg2"])
+    m = int(c["m"] * scale) * n_gpus
+    n = int(c["n"] * scale)
+    # homologous segments follow the main diagonal of the first 5M x 5M square (cfg2), the extra rows of the
+    # weak-scaling variants are unrelated sequence
+    segs = [(int(a0 * scale), int(a1 * scale)) for a0, a1 in c["segs"]]
+    K = c["K"] if scale == 1.0 else int(c["K"] * scale)
+    a, b = synth.make_pair(m, n, segs, c["p_s"], c["p_d"], c["p_i"], K, c["seed"], int(c.get("shift", 0) * scale))
+    return a, b
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+        self.marks = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, windows):
+        sm, mx, reasons = [], 0.0, set()
+        for ts, line in self.rows:
+            if not any(t0 <= ts <= t1 for t0, t1 in windows):
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def inst_per_cell(kernel_used):
+    """SASS thread-instructions per DP cell of the dominant kernel, from the committed ncu summary."""
+    p = os.path.join(ROOT, "profiles", "r01_inst_per_cell.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("s16x2" if kernel_used == 2 else "s32"), d
+    return None, {}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref, built from /root/reference sources)
+# ------------------------------------------------------------------------------------------------------------
+def ref_binary():
+    p = os.path.join(ROOT, "oracle", "_ref", "oracle_cpu_block")
+    return p if os.path.exists(p) else None
+
+
+def run_reference_sample(a, b, rows, cols, cores, workdir):
+    """Time the reference CPU path (CPUBlockProcessor via AbstractBlockAligner, --fork over `cores` processes)
+    on the top-left rows x cols sample of the workload.  Returns (seconds of stage 1, cells)."""
+    import synth
+    fa, fb = os.path.join(workdir, "A.fa"), os.path.join(workdir, "B.fa")
+    synth.write_fasta(fa, a[:rows], "bench_A")
+    synth.write_fasta(fb, b[:cols], "bench_B")
+    exe = ref_binary()
+    cmd = [exe, f"--work-dir={os.path.join(workdir, 'w')}", "--clear", "--verbose=0", "--stage-1", "--no-flush"]
+    if cores > 1:
+        cmd.append(f"--fork={cores}")
+    else:
+        cmd.append("--no-block-pruning")      # --fork force-disables pruning (libmasa.cpp:1318-1321): keep both modes comparable
+    cmd += [fa, fb]
+    t0 = time.perf_counter()
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, cwd=workdir)
+    dt = time.perf_counter() - t0
+    return dt, rows * cols
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    if ref_binary() is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/oracle_cpu_block not built (reference mount absent at build time)"}))
+        return 0
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    a, b = make_workload(args.gpus, args.scale)
+    m, n = a.size, b.size
+    # bounded sample: ~1.2e9 cells per core per step (about 5-8 s at the reference's ~0.2 GCUPS/core)
+    side = int(min(m, n, (1.2e9 * cores) ** 0.5))
+    side = max(2000, side)
+    times = []
+    with tempfile.TemporaryDirectory() as td:
+        for it in range(args.warmup + args.steps):
+            dt, cells = run_reference_sample(a, b, side, side, cores, td)
+            if it >= args.warmup:
+                times.append(dt)
+            log(f"[reference] step {it}: {side}x{side} in {dt:.2f}s = {cells/dt/1e9:.3f} GCUPS on {cores} cores")
+    total = sum(times)
+    val = side * side * len(times) / total / 1e9
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus, m, n), "sample": f"top-left {side}x{side} cells per step"},
+        "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": "reference",
+                         "sample": f"oracle/_ref/oracle_cpu_block --stage-1 --fork={cores} on the top-left {side}x{side} of the workload (process wall time)"},
+        "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_name(n_gpus, m, n):
+    if n_gpus == 1:
+        return f"cfg2: {m}x{n} synthetic bacterial-genome-shaped pair (seed 0xC0DA0002), SW stage-1 best score + end coordinate"
+    return (f"cfg2 weak-scaled: {m}x{n} ({n_gpus} x 5M rows, 5M columns split into {n_gpus} column slices, chained wavefront), "
+            "SW stage-1 best score + end coordinate")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only; the default 1.0 is the benchmark)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "s32", "s16x2"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import numpy as np
+    import torch
+    from __graft_entry__ import load_package
+    b200 = load_package()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            log(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks")
+            return 2
+    if not torch.cuda.is_available():
+        log("bench.py: no CUDA device; the product path has no CPU fallback")
+        return 2
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    a, b = make_workload(args.gpus, args.scale)
+    m, n = a.size, b.size
+    kern = {"auto": b200.KERNEL_AUTO, "s32": b200.KERNEL_S32, "s16x2": b200.KERNEL_S16X2}[args.kernel]
+    al = b200.Aligner(device=local, kernel=kern)
+    j0, j1 = n * rank // world, n * (rank + 1) // world           # column slice of this rank (libmasa.cpp:632-635)
+    if world > 1:
+        al.mgpu_setup(dist, rank, world, m)
+    al.set_sequences(a, b)                                         # sequences resident in HBM for the `value` leg
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def one_step(e2e):
+        if e2e:
+            al.set_sequences(a, b)                                 # H2D of both sequences from host memory
+        if world > 1:
+            return al.align_partition(0, j0, m, j1, want_best_score=True, use_callbacks=False, mgpu=True)
+        return al.align_partition(0, j0, m, j1, want_best_score=True, use_callbacks=False)
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    res = None
+    for _ in range(args.warmup):
+        flush.zero_()
+        barrier()
+        res = one_step(False)
+    launches0 = al.kernel_launches()
+    windows, step_times, dev_ms = [], [], []
+    for _ in range(args.steps):
+        flush.zero_()                                              # L2 flush between timed iterations (untimed)
+        barrier()
+        w0 = time.time(); t0 = time.perf_counter()
+        res = one_step(False)
+        barrier()
+        t1 = time.perf_counter(); w1 = time.time()
+        step_times.append(t1 - t0); dev_ms.append(res["device_ms"]); windows.append((w0, w1))
+    launches = al.kernel_launches() - launches0
+    # e2e leg: same metric through the public C ABI with HOST buffers (sequence upload + result read-back timed)
+    e2e_times = []
+    for _ in range(max(1, min(args.steps, 2))):
+        flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
+        res_e = one_step(True)
+        barrier()
+        e2e_times.append(time.perf_counter() - t0)
+    sampler.stop()
+
+    total = sum(step_times)
+    e2e_total = sum(e2e_times)
+    if dist is not None:
+        t = torch.tensor([total, e2e_total, sum(dev_ms) / 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total, e2e_total, dev_total = (float(x) for x in t.tolist())
+        bests = [None] * world
+        dist.all_gather_object(bests, tuple(res["best"]))
+        best = max(bests, key=lambda s: (s[0], -s[1], -s[2]))
+        cells_t = torch.tensor([res["cells"]], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cells_t)
+        cells = int(cells_t.item())
+    else:
+        dev_total = sum(dev_ms) / 1e3
+        best = tuple(res["best"])
+        cells = res["cells"]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    K = len(step_times)
+    value = m * n * K / total / 1e9
+    clocks = sampler.summary(windows)
+    peaks, peak_src = measured_peaks()
+    kernel_used = res["kernel_used"]
+    ipc, ipc_doc = inst_per_cell(kernel_used)
+    f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
+    kernel_gcups = m * n * K / dev_total / 1e9 / args.gpus            # per GPU, kernel time from CUDA events on the launch stream
+    roofline = {"bound": "int-issue", "unit": "GCUPS", "achieved": kernel_gcups, "traffic": ipc_doc.get("dram_bytes_per_launch")}
+    if ipc:
+        peak = 148 * 4 * 32 * f_mhz * 1e6 / ipc / 1e9
+        roofline.update({"peak": peak, "frac": kernel_gcups / peak, "inst_per_cell": ipc,
+                         "peak_def": f"148 SMs x 4 schedulers x 32 lanes x {f_mhz:.0f} MHz (median SM clock sampled under load) / {ipc} SASS thread-instr per cell (ncu, profiles/)"})
+        alu = ipc_doc.get("alu_slots_per_cell_s16x2" if kernel_used == 2 else "alu_slots_per_cell_s32")
+        if alu:
+            apeak = 148 * 64 * f_mhz * 1e6 / alu / 1e9
+            roofline.update({"alu_pipe_peak": apeak, "alu_pipe_frac": kernel_gcups / apeak,
+                             "alu_pipe_def": f"148 SMs x 64 lanes/clk (measured VIADDMNMX/VIMNMX issue rate, profiles/r01_pipe_rates.txt) / {alu} ALU-pipe slots per cell"})
+    # HBM is not the bound: algorithmic border traffic (16 B per column per strip + 1 B of seq1) vs the measured copy peak
+    strips = res["strips"]
+    alg_bytes = strips * (j1 - j0) * 17.0
+    roofline["hbm"] = {"achieved_gbs": alg_bytes * K / dev_total / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
+        "ms_per_step": total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int16x2" if kernel_used == 2 else "int32", "data": "synthetic",
+        "config": {"workload": workload_name(args.gpus, m, n), "m": m, "n": n, "recurrence": "SW affine +1/-3/-3/-2",
+                   "l2": "256 MiB flush buffer written between timed iterations", "kernel": "s16x2" if kernel_used == 2 else "s32",
+                   "strips_per_gpu": strips, "best": list(best), "cells_computed": cells,
+                   "published_other_hw": "README: 5Mx5M 48.98 GCUPS on GTX 560 Ti (all stages); 249Mx228M 82,822 GCUPS on 512xV100"},
+        "device_ms_per_step": dev_total / K * 1e3,
+        "clocks": clocks,
+        "e2e": {"value": m * n * len(e2e_times) / e2e_total / 1e9, "unit": "GCUPS",
+                "h2d_bytes_per_step": int(m + n), "d2h_bytes_per_step": int(strips * 16 + 32)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if not args.no_cpu_baseline and ref_binary() is not None:
+        side = int(min(m, n, 50_000 * max(args.scale, 0.02) ** 0.0))
+        side = min(side, 60_000)
+        with tempfile.TemporaryDirectory() as td:
+            dt, c = run_reference_sample(a, b, side, side, 1, td)
+        line["cpu_baseline"] = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference",
+                                "sample": f"oracle/_ref/oracle_cpu_block --stage-1 --no-block-pruning (reference CPUBlockProcessor, 1 core) on the top-left {side}x{side} of the workload, {dt:.1f}s"}
+    elif not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        side = min(m, n, 20_000)
+        t0 = time.perf_counter()
+        O.full_matrix(a[:side], b[:side], O.SW, want_last_col=False)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": side * side / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
+                                "sample": f"oracle/gotoh_oracle.c scalar port on the top-left {side}x{side}, {dt:.1f}s"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -133,6 +133,23 @@ int b200_diag_end(b200_handle* h);                                              
 int b200_match_last_column(b200_handle* h, const b200_cell* buffer, const b200_cell* base, int len, int goal,
                            b200_match* out);
 
+/* Multi-GPU chained wavefront on one NVLink/NVSwitch box: one process (and one b200_handle) per GPU, seq1 split
+ * into contiguous column slices exactly like the reference's --fork/--split (C/libmasa/libmasa.cpp:540-642), but
+ * the slice-border column never touches the host or a socket (reference: SocketCellsWriter/Reader + Buffer2,
+ * C/stage1/sw_stage1.cpp:168-186): the strip kernel of GPU g stores its right border straight into the
+ * exchange block of GPU g+1 (peer memory, P2P stores) and releases a system-scope row counter that the strip
+ * warps of g+1 acquire before they load their left border.  The running best score is pushed to every peer
+ * (peer atomicMax), replacing AlignerPool's file+signal polling (C/common/AlignerPool.cpp:46-68).
+ *   1. every rank: b200_mgpu_export(h, max_rows, &mine)
+ *   2. exchange the 64-byte handles out of band (torch.distributed all_gather in bench.py)
+ *   3. every rank: b200_mgpu_connect(h, rank, world, all_handles)
+ *   4. every rank: b200_align_partition with b200_partition.reserved[0] = B200_MGPU_CHAIN on its own slice */
+typedef struct { unsigned char bytes[64]; } b200_ipc_handle;
+#define B200_MGPU_CHAIN 1
+int b200_mgpu_export(b200_handle* h, int max_rows, b200_ipc_handle* out);
+int b200_mgpu_connect(b200_handle* h, int rank, int world, const b200_ipc_handle* all_handles);
+int b200_mgpu_disconnect(b200_handle* h);
+
 /* statistics (IAligner::getProcessedCells etc.) */
 long long b200_processed_cells(const b200_handle* h);
 long long b200_kernel_launches(const b200_handle* h);

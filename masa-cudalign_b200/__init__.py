@@ -62,7 +62,7 @@ EXPORTS = [
     "b200_unset_sequences", "b200_align_partition", "b200_diag_begin", "b200_diag_set_first_row",
     "b200_diag_set_first_column", "b200_diag_process", "b200_diag_get_row", "b200_diag_get_last_column",
     "b200_diag_get_block_scores", "b200_diag_clear_pruned", "b200_diag_end", "b200_match_last_column",
-    "b200_processed_cells", "b200_kernel_launches",
+    "b200_processed_cells", "b200_kernel_launches", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect",
 ]
 
 _lib = None
@@ -96,6 +96,9 @@ def load_library(path=None):
     lib.b200_processed_cells.restype = C.c_longlong
     lib.b200_kernel_launches.argtypes = [C.c_void_p]
     lib.b200_kernel_launches.restype = C.c_longlong
+    lib.b200_mgpu_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200_mgpu_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.b200_mgpu_disconnect.argtypes = [C.c_void_p]
     if path is None:
         _lib = lib
     return lib
@@ -146,7 +149,7 @@ class Aligner:
     def align_partition(self, i0=0, j0=0, i1=None, j1=None, recurrence=SMITH_WATERMAN, first_row_init=INIT_ZEROES,
                         first_col_init=INIT_ZEROES, first_row=None, first_col=None, special_row_interval=0,
                         block_height=0, want_special_rows=False, want_last_row=False, want_last_column=False,
-                        want_best_score=True, prune=False, use_callbacks=True):
+                        want_best_score=True, prune=False, use_callbacks=True, mgpu=False):
         """Run b200_align_partition.  first_row / first_col: CELL arrays INCLUDING the corner as element 0
         (n+1 / m+1 cells), used when the init type is INIT_CUSTOM (or to feed gaps through the callback path)."""
         a, b = self._seqs
@@ -157,6 +160,8 @@ class Aligner:
                          block_height=block_height, want_special_rows=int(want_special_rows),
                          want_last_row=int(want_last_row), want_last_column=int(want_last_column),
                          want_best_score=int(want_best_score), prune=int(prune), super_i1=i1, super_j1=j1)
+        if mgpu:
+            part.reserved[0] = 1          # B200_MGPU_CHAIN
         out = {"rows": {}, "row_first": {}, "last_column": [], "scores": []}
         pos = {"row": 0, "col": 0}
 
@@ -207,6 +212,16 @@ class Aligner:
         out["rows"] = {i: np.concatenate(v) for i, v in out["rows"].items()}
         out["last_column"] = np.concatenate(out["last_column"]) if out["last_column"] else np.zeros(0, CELL)
         return out
+
+    # ---- multi-GPU chain -----------------------------------------------------------------------------
+    def mgpu_setup(self, dist, rank, world, max_rows):
+        """Export this rank's exchange block, all-gather the IPC handles over torch.distributed, map the peers."""
+        mine = (C.c_ubyte * 64)()
+        self._check(self.lib.b200_mgpu_export(self.h, max_rows, mine), "b200_mgpu_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine))
+        blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
+        self._check(self.lib.b200_mgpu_connect(self.h, rank, world, blob), "b200_mgpu_connect")
 
     # ---- diag primitives -------------------------------------------------------------------------------
     def diag_begin(self, part: Partition, split, block_height):

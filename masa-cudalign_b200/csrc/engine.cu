@@ -93,6 +93,22 @@ struct b200_handle {
 		std::vector<b200_score> scores;
 	} dg;
 
+	// multi-GPU chain: exchange block = [64 control ints][max_rows+1 cells]; ctrl[0] = rows of our left border
+	// delivered by the previous GPU, ctrl[1] = running best shared by all GPUs
+	struct {
+		int* block = nullptr;
+		size_t max_rows = 0;
+		int rank = -1, world = 0;
+		int* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+		bool connected = false;
+	} mg;
+	// per-launch overrides of the border / sharing pointers (diag mode and chain mode)
+	struct {
+		const Cell* left = nullptr; Cell* right = nullptr;
+		const int* left_ready = nullptr; int* right_ready = nullptr;
+		int* gbest = nullptr; int* peer_best[8]; int npeer = 0;
+	} ov;
+
 	long long stat_cells = 0;
 	long long stat_launches = 0;
 };
@@ -177,10 +193,15 @@ int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kernel_kind, int SH, bool chained) {
 	StripParams sp;
 	sp.s0 = h->s0.p; sp.s1 = h->s1.p;
-	sp.busH = h->busH.p; sp.left = h->left.p; sp.right = h->right.p; sp.sra = h->sra.p;
+	sp.busH = h->busH.p; sp.sra = h->sra.p;
+	sp.left = h->ov.left ? h->ov.left : h->left.p;
+	sp.right = h->ov.right ? h->ov.right : h->right.p;
+	sp.left_ready = h->ov.left_ready; sp.right_ready = h->ov.right_ready;
+	sp.n_peer_best = h->ov.npeer;
+	for (int k = 0; k < 8; k++) sp.peer_best[k] = k < h->ov.npeer ? h->ov.peer_best[k] : nullptr;
 	sp.jobs = h->jobs.p; sp.njobs = njobs;
 	sp.job_counter = h->scalars.p + 0;
-	sp.global_best = h->scalars.p + 1;
+	sp.global_best = h->ov.gbest ? h->ov.gbest : h->scalars.p + 1;
 	sp.stop_flag = h->scalars.p + 2;
 	sp.cells_done = reinterpret_cast<unsigned long long*>(h->scalars.p + 4);
 	sp.progress = h->progress.p;
@@ -266,6 +287,7 @@ extern "C" int b200_create(const b200_config* cfg, b200_handle** out) {
 	return 0;
 }
 
+extern "C" int b200_mgpu_disconnect(b200_handle* h);
 extern "C" void b200_destroy(b200_handle* h) {
 	if (!h) return;
 	cudaSetDevice(h->cfg.device);
@@ -274,6 +296,7 @@ extern "C" void b200_destroy(b200_handle* h) {
 	h->jobs.release(); h->progress.release(); h->results.release(); h->scalars.release();
 	h->hcells.release(); h->hresults.release(); h->hscalars.release();
 	h->dg.vbuf.release(); h->dg.col0.release();
+	b200_mgpu_disconnect(h);
 	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
 	delete h;
@@ -342,6 +365,10 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	const int SH = strip_height(kind, true);
 	const bool sw = p->recurrence == B200_SMITH_WATERMAN;
 	const int track = p->want_best_score ? 2 : 0;
+	const bool chain = (p->reserved[0] & B200_MGPU_CHAIN) != 0;
+	if (chain && (!h->mg.connected || (size_t)m > h->mg.max_rows)) { h->err = "b200_align_partition: multi-GPU chain requested but b200_mgpu_connect was not called (or max_rows too small)"; return 1; }
+	const bool left_remote = chain && h->mg.rank > 0;
+	const bool right_remote = chain && h->mg.rank + 1 < h->mg.world;
 
 	// ---- special rows and strips
 	int bh = p->block_height > 0 ? p->block_height : 4 * std::min(128, n);
@@ -363,9 +390,9 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			memset(&j, 0, sizeof(j));
 			j.i0 = p->i0 + r; j.rows = end - r; j.j0 = p->j0; j.cols = n;
 			j.dep = (int)h->hjobs.size() - 1;
-			j.flags = (p->first_col_init == B200_INIT_ZEROES) ? JOB_LEFT_ZERO : 0;
+			j.flags = (p->first_col_init == B200_INIT_ZEROES && !left_remote) ? JOB_LEFT_ZERO : 0;
 			j.left_off = r;
-			j.right_off = p->want_last_column ? r : -1;
+			j.right_off = (p->want_last_column || right_remote) ? r : -1;
 			j.sra_off = sra_off;
 			h->hjobs.push_back(j);
 			r = end;
@@ -395,16 +422,16 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	Cell first_row_tail = corner_row;
 	if (p->first_row_init == B200_INIT_ZEROES || !(have_cb && cb->receive_first_row)) {
 		int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
-		fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1, 0);
+		fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1 + p->reserved[1], 0);   // reserved[1]: column offset of a chained slice
 		h->stat_launches++;
-		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * n - (type == B200_INIT_GAPS ? kGapOpen : 0);
+		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * (n + p->reserved[1]) - (type == B200_INIT_GAPS ? kGapOpen : 0);
 	} else {
 		cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p), n);
 		first_row_tail = h->hcells.p[n - 1];
 		CU(h, cudaMemcpyAsync(h->busH.p + p->j0, h->hcells.p, (size_t)n * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 		CU(h, cudaStreamSynchronize(h->stream));
 	}
-	if (p->first_col_init != B200_INIT_ZEROES) {
+	if (p->first_col_init != B200_INIT_ZEROES && !left_remote) {
 		CU(h, h->left.reserve((size_t)m + 1));
 		if (have_cb && cb->receive_first_column) {
 			h->hcells.p[0] = corner_col;
@@ -419,8 +446,22 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	}
 
 	// ---- the alignment itself: one persistent launch
+	if (chain) {
+		Cell* my_cells = reinterpret_cast<Cell*>(h->mg.block + 64);
+		if (left_remote) { h->ov.left = my_cells; h->ov.left_ready = h->mg.block + 0; }
+		if (right_remote) {
+			int* nb = h->mg.peers[h->mg.rank + 1];
+			h->ov.right = reinterpret_cast<Cell*>(nb + 64);
+			h->ov.right_ready = nb + 0;
+		}
+		h->ov.gbest = h->mg.block + 1;
+		h->ov.npeer = 0;
+		for (int r = 0; r < h->mg.world; r++) if (r != h->mg.rank) h->ov.peer_best[h->ov.npeer++] = h->mg.peers[r] + 1;
+	}
 	CU(h, cudaEventRecord(h->ev0, h->stream));
-	if (launch_strips(h, njobs, p->recurrence, track, kind, SH, true)) return 1;
+	int lrc = launch_strips(h, njobs, p->recurrence, track, kind, SH, true);
+	h->ov.left = nullptr; h->ov.right = nullptr; h->ov.left_ready = nullptr; h->ov.right_ready = nullptr; h->ov.gbest = nullptr; h->ov.npeer = 0;
+	if (lrc) return 1;
 	CU(h, cudaEventRecord(h->ev1, h->stream));
 	if (track) CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -429,6 +470,11 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	float ms = 0;
 	CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 
+	if (chain) {
+		// re-arm the exchange block for the next chained call; the caller barriers the ranks between calls
+		CU(h, cudaMemsetAsync(h->mg.block, 0, 2 * sizeof(int), h->stream));
+		CU(h, cudaStreamSynchronize(h->stream));
+	}
 	out->device_ms = ms;
 	out->strips = njobs;
 	out->kernel_launches = 1;
@@ -477,7 +523,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 				cb->dispatch_row(cb->ctx, p->i1, reinterpret_cast<b200_cell*>(h->hcells.p), n);
 			}
 		}
-		if (cb->dispatch_column && p->want_last_column) {
+		if (cb->dispatch_column && p->want_last_column && !right_remote) {
 			CU(h, cudaMemcpy(h->hcells.p, h->right.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyDeviceToHost));
 			b200_cell fc; fc.h = first_row_tail.h; fc.x = -kInf;
 			cb->dispatch_column(cb->ctx, p->j1, &fc, 1);
@@ -588,10 +634,9 @@ extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, 
 	if (njobs == 0) return 0;
 	if (reset_scalars(h, -kInf)) return 1;
 	CU(h, cudaMemcpyAsync(h->jobs.p, h->hjobs.data(), njobs * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
-	Cell* save_left = h->left.p; Cell* save_right = h->right.p;
-	h->left.p = d.vbuf.p; h->right.p = d.vbuf.p;
+	h->ov.left = d.vbuf.p; h->ov.right = d.vbuf.p;
 	int rc = launch_strips(h, njobs, p.recurrence, 1, kind, SH, false);
-	h->left.p = save_left; h->right.p = save_right;
+	h->ov.left = nullptr; h->ov.right = nullptr;
 	if (rc) return 1;
 	CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -676,5 +721,53 @@ extern "C" int b200_match_last_column(b200_handle* h, const b200_cell* buffer, c
 		else if (kindc == 1) { out->found = 1; out->score = base[k].x; out->type = 1; }
 		else { out->found = 0; out->type = kindc == 2 ? -1 : -2; }
 	}
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// multi-GPU chain
+// ---------------------------------------------------------------------------------------------------------
+static_assert(sizeof(b200_ipc_handle) >= sizeof(cudaIpcMemHandle_t), "ipc handle size");
+
+extern "C" int b200_mgpu_export(b200_handle* h, int max_rows, b200_ipc_handle* out) {
+	if (!h) return 1;
+	if (!out || max_rows <= 0) { h->err = "b200_mgpu_export: bad arguments"; return 1; }
+	CU(h, cudaSetDevice(h->cfg.device));
+	if (h->mg.block) { cudaFree(h->mg.block); h->mg.block = nullptr; }
+	size_t bytes = 64 * sizeof(int) + ((size_t)max_rows + 2) * sizeof(Cell);
+	CU(h, cudaMalloc((void**)&h->mg.block, bytes));
+	CU(h, cudaMemset(h->mg.block, 0, bytes));
+	h->mg.max_rows = (size_t)max_rows;
+	cudaIpcMemHandle_t ih;
+	CU(h, cudaIpcGetMemHandle(&ih, h->mg.block));
+	memset(out, 0, sizeof(*out));
+	memcpy(out->bytes, &ih, sizeof(ih));
+	return 0;
+}
+
+extern "C" int b200_mgpu_connect(b200_handle* h, int rank, int world, const b200_ipc_handle* all_handles) {
+	if (!h) return 1;
+	if (!all_handles || world < 1 || world > 8 || rank < 0 || rank >= world || !h->mg.block) { h->err = "b200_mgpu_connect: bad arguments (world <= 8, export first)"; return 1; }
+	CU(h, cudaSetDevice(h->cfg.device));
+	for (int r = 0; r < world; r++) {
+		h->mg.peers[r] = nullptr;
+		if (r == rank) { h->mg.peers[r] = h->mg.block; continue; }
+		cudaIpcMemHandle_t ih;
+		memcpy(&ih, all_handles[r].bytes, sizeof(ih));
+		void* ptr = nullptr;
+		CU(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
+		h->mg.peers[r] = reinterpret_cast<int*>(ptr);
+	}
+	h->mg.rank = rank; h->mg.world = world; h->mg.connected = true;
+	return 0;
+}
+
+extern "C" int b200_mgpu_disconnect(b200_handle* h) {
+	if (!h) return 1;
+	if (h->mg.connected)
+		for (int r = 0; r < h->mg.world; r++)
+			if (r != h->mg.rank && h->mg.peers[r]) cudaIpcCloseMemHandle(h->mg.peers[r]);
+	h->mg.connected = false;
+	if (h->mg.block) { cudaFree(h->mg.block); h->mg.block = nullptr; }
 	return 0;
 }

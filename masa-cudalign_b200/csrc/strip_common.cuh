@@ -59,6 +59,10 @@ struct StripParams {
 	int* global_best;       // running best score of the whole partition (atomicMax)
 	unsigned long long* cells_done;   // statistics
 	const int* stop_flag;   // host-mapped: non-zero asks the kernel to stop claiming jobs
+	const int* left_ready;  // multi-GPU: rows of our left border published by the previous GPU (system scope), or NULL
+	int* right_ready;       // multi-GPU: row counter in the NEXT GPU's exchange block (peer memory), or NULL
+	int* peer_best[8];      // multi-GPU: running-best words of the other GPUs (peer memory)
+	int n_peer_best;
 	int recurrence;         // B200_SMITH_WATERMAN | B200_NEEDLEMAN_WUNSCH
 	int track;              // 0: no best tracking; 1: exact best cell per job; 2: per job, thresholded by global_best
 };
@@ -75,6 +79,36 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
 	int v;
 	asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
 	return v;
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+	int v;
+	asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+	asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until the previous GPU has delivered rows [.., upto) of our left border (lane 0 spins, warp follows)
+__device__ __forceinline__ void wait_left(const StripParams& p, int upto, int lane) {
+	if (p.left_ready == nullptr) return;
+	if (lane == 0) {
+		while (ld_acquire_sys(p.left_ready) < upto) {
+			if (ld_relaxed(p.stop_flag)) break;
+			__nanosleep(256);
+		}
+	}
+	__syncwarp();
+}
+// publish our finished right-border rows to the next GPU; called before the strip's final progress release so
+// that publications of consecutive strips are ordered
+__device__ __forceinline__ void publish_right(const StripParams& p, int upto, int lane) {
+	if (p.right_ready == nullptr) return;
+	__syncwarp();
+	if (lane == 0) { __threadfence_system(); st_release_sys(p.right_ready, upto); }
+}
+__device__ __forceinline__ void push_best(const StripParams& p, int v) {
+	atomicMax(p.global_best, v);
+	for (int k = 0; k < p.n_peer_best; k++) atomicMax_system(p.peer_best[k], v);
 }
 __device__ __forceinline__ Cell ldcg_cell(const Cell* p) {
 	int2 v = __ldcg(reinterpret_cast<const int2*>(p));

@@ -220,6 +220,7 @@ struct StripS16 {
 		const int vo = (rows - 1) / R, ro = (rows - 1) % R;
 
 		State s;
+		if (!(jb.flags & JOB_LEFT_ZERO)) wait_left(p, jb.left_off + rows, lane);
 		// ---- left border; the frame starts at the H of the corner
 		const Cell* lb = p.left + jb.left_off;
 		const bool lz = (jb.flags & JOB_LEFT_ZERO) != 0;
@@ -310,7 +311,7 @@ struct StripS16 {
 				sm.prof[warp][lane] = pw;
 				if (TRACK && p.track == 2) {
 					// share the running best: publish ours, adopt a higher one (monotone, staleness is harmless)
-					if (s.thr > s.pub) { if (lane == 0) atomicMax(p.global_best, s.thr); s.pub = s.thr; }
+					if (s.thr > s.pub) { if (lane == 0) push_best(p, s.thr); s.pub = s.thr; }
 					const int g = ld_relaxed(p.global_best);
 					if (g > s.thr) { s.thr = g; s.pub = g; s.thrp = thr_pack(s.thr, s.base); }
 				}
@@ -340,6 +341,7 @@ struct StripS16 {
 					if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, hv, fv);
 				}
 				flushed = cdone + 1;
+				if (flushed == cols && jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
 				__syncwarp();
 				if (lane == 0) { __threadfence(); st_release(p.progress + job, flushed); }
 			}
@@ -357,7 +359,7 @@ struct StripS16 {
 			if (lane == 0) {
 				Score3 o; o.score = bs == INT_MIN ? -kInf : bs; o.i = bi; o.j = bj; o.pad = 0;
 				p.results[job] = o;
-				if (bs != INT_MIN) atomicMax(p.global_best, bs);
+				if (bs != INT_MIN) push_best(p, bs);
 			}
 		}
 		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)cols);
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) strip_kernel_s16(const St
 			if (jb.right_off >= 0)
 				for (int k = lane; k <= jb.rows; k += 32) stcg_cell(p.right + jb.right_off + k, -kInf, -kInf);
 			if (TRACK && lane == 0) { Score3 o; o.score = -kInf; o.i = -1; o.j = -1; o.pad = 0; p.results[job] = o; }
+			if (jb.right_off >= 0) publish_right(p, jb.left_off + jb.rows, lane);
 			__syncwarp();
 			if (lane == 0) { __threadfence(); st_release(p.progress + job, jb.cols); }
 			continue;

@@ -34,6 +34,7 @@ struct StripS32 {
 			if (jb.right_off >= 0)
 				for (int k = lane; k <= rows; k += 32) stcg_cell(p.right + jb.right_off + k, -kInf, -kInf);
 			if (TRACK && lane == 0) { Score3 s; s.score = -kInf; s.i = -1; s.j = -1; s.pad = 0; p.results[job] = s; }
+			if (jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
 			__threadfence(); __syncwarp();
 			if (lane == 0) st_release(p.progress + job, cols);
 			return;
@@ -49,6 +50,7 @@ struct StripS32 {
 		for (int r = 0; r < R; r++) c0[r] = (r < nvalid) ? (int)p.s0[i0 + row_base + r] : 0x100;   // 0x100 never equals a byte
 
 		int tprev;   // H(row above this lane, previous column) - 5: diagonal term of row 0
+		if (!(jb.flags & JOB_LEFT_ZERO)) wait_left(p, jb.left_off + rows, lane);
 		if (jb.flags & JOB_LEFT_ZERO) {
 #pragma unroll
 			for (int r = 0; r < R; r++) { T[r] = 0 - kGapFirst; E[r] = -kInf; }
@@ -93,7 +95,7 @@ struct StripS32 {
 				sm.top[warp][lane] = tv;
 				sm.seq[warp][lane] = ch;
 				if (TRACK && p.track == 2) {
-					if (thr > pub) { if (lane == 0) atomicMax(p.global_best, thr); pub = thr; }
+					if (thr > pub) { if (lane == 0) push_best(p, thr); pub = thr; }
 					const int g = ld_relaxed(p.global_best);
 					if (g > thr) { thr = g; pub = g; }
 				}
@@ -170,6 +172,7 @@ struct StripS32 {
 					if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, v.h, v.x);
 				}
 				flushed = cdone + 1;
+				if (flushed == cols && jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
 				__threadfence();
 				__syncwarp();
 				if (lane == 0) st_release(p.progress + job, flushed);
@@ -187,7 +190,7 @@ struct StripS32 {
 			if (lane == 0) {
 				Score3 s; s.score = bs == INT_MIN ? -kInf : bs; s.i = bi; s.j = bj; s.pad = 0;
 				p.results[job] = s;
-				if (bs != INT_MIN) atomicMax(p.global_best, bs);
+				if (bs != INT_MIN) push_best(p, bs);
 			}
 		}
 		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)cols);
