@@ -165,9 +165,10 @@ __global__ void match_column_kernel(const Cell* buffer, const Cell* base, int le
 // Grid of the persistent strip kernel.  All CTAs must be co-resident (a strip spins on the progress of the
 // strip above it), so the grid never exceeds SMs x occupancy.  Below that limit the number of resident warps
 // per SM is chosen so that the strips fill whole waves: every strip sweeps the full width at the pace of one
-// warp, so a last, nearly empty wave would cost as much as a full one.  kSatWarps is the measured number of
-// strip-warps that saturate an SM's VIADDMNMX pipe (profiles/r01_*): more warps only stretch each wave.
-constexpr int kSatWarps = 7;
+// warp, so a last, nearly empty wave would cost as much as a full one.  kSatWarps: resident strip-warps per SM
+// beyond which the measured throughput no longer grows (ALU pipe ~75% busy in steady state, profiles/r01_*):
+// more warps only stretch each wave.
+constexpr int kSatWarps = 11;
 int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 	int per_sm = 0;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, 0);

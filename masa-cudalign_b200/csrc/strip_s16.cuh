@@ -367,7 +367,7 @@ struct StripS16 {
 };
 
 template <int R, bool SW, bool TRACK>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) strip_kernel_s16(const StripParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 12) strip_kernel_s16(const StripParams p) {
 	using K = StripS16<R, SW, TRACK>;
 	__shared__ typename K::Smem sm;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
