@@ -50,7 +50,7 @@ extern "C" {
 #define B200_KERNEL_S16X2 2           /* packed s16x2 DPX lanes with per-block rebasing; ACGT only */
 
 typedef struct { int h; int x; } b200_cell;          /* == cell_t: x is F in rows, E in columns */
-typedef struct { int score; int i; int j; } b200_score;   /* == score_t, 0-based (C/libmasa/libmasaTypes.hpp:88-95) */
+typedef struct { int i; int j; int score; } b200_score;   /* == score_t field for field, 0-based (C/libmasa/libmasaTypes.hpp:88-95) */
 typedef struct { int found; int k; int score; int type; } b200_match;   /* == match_result_t (:51-60) */
 
 typedef struct {

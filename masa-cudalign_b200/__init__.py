@@ -33,7 +33,7 @@ class Partition(C.Structure):
 
 
 class Score(C.Structure):
-    _fields_ = [("score", C.c_int), ("i", C.c_int), ("j", C.c_int)]
+    _fields_ = [("i", C.c_int), ("j", C.c_int), ("score", C.c_int)]
 
 
 class Match(C.Structure):
@@ -250,7 +250,7 @@ class Aligner:
         return out
 
     def diag_get_block_scores(self, B):
-        out = np.zeros(B, np.dtype([("score", "<i4"), ("i", "<i4"), ("j", "<i4")]))
+        out = np.zeros(B, np.dtype([("i", "<i4"), ("j", "<i4"), ("score", "<i4")]))
         self._check(self.lib.b200_diag_get_block_scores(self.h, out.ctypes.data), "b200_diag_get_block_scores")
         return out
 

@@ -571,7 +571,10 @@ extern "C" int b200_diag_begin(b200_handle* h, const b200_partition* p, int grid
 }
 
 extern "C" int b200_diag_set_first_row(b200_handle* h, const b200_cell* cells, int j, int len) {
-	if (!h || !h->dg.active) return 1;
+	// AbstractDiagonalAligner::prepareIterations loads the first row BEFORE initializeDiagonals
+	// (AbstractDiagonalAligner.cpp:89,103), so this call only needs the sequences (busH), not an open diag session.
+	if (!h) return 1;
+	CU(h, cudaSetDevice(h->cfg.device));
 	if (!cells || j < 0 || len < 0 || j + len > h->n1) { h->err = "b200_diag_set_first_row: bad range"; return 1; }
 	CU(h, cudaMemcpyAsync(h->busH.p + j, cells, (size_t)len * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
@@ -579,7 +582,8 @@ extern "C" int b200_diag_set_first_row(b200_handle* h, const b200_cell* cells, i
 }
 
 extern "C" int b200_diag_set_first_column(b200_handle* h, const b200_cell* cells, int i, int len) {
-	if (!h || !h->dg.active) return 1;
+	if (!h) return 1;
+	if (!h->dg.active) { h->err = "diag primitive called outside b200_diag_begin/b200_diag_end"; return 1; }
 	auto& d = h->dg;
 	(void)i; (void)len;
 	// cells[0] = diagonal cell, cells[1..bh] = (H,E) of the chunk; consumed by block (0, by) one call later
@@ -592,7 +596,8 @@ extern "C" int b200_diag_set_first_column(b200_handle* h, const b200_cell* cells
 }
 
 extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, int window_right) {
-	if (!h || !h->dg.active) return 1;
+	if (!h) return 1;
+	if (!h->dg.active) { h->err = "diag primitive called outside b200_diag_begin/b200_diag_end"; return 1; }
 	CU(h, cudaSetDevice(h->cfg.device));
 	auto& d = h->dg;
 	const b200_partition& p = d.part;
@@ -653,7 +658,8 @@ extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, 
 }
 
 extern "C" int b200_diag_get_row(b200_handle* h, int j, int len, b200_cell* out) {
-	if (!h || !h->dg.active) return 1;
+	if (!h) return 1;
+	if (!h->dg.active) { h->err = "diag primitive called outside b200_diag_begin/b200_diag_end"; return 1; }
 	if (!out || j < 0 || len < 0 || j + len > h->n1) { h->err = "b200_diag_get_row: bad range"; return 1; }
 	CU(h, cudaMemcpyAsync(out, h->busH.p + j, (size_t)len * sizeof(Cell), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
@@ -661,7 +667,8 @@ extern "C" int b200_diag_get_row(b200_handle* h, int j, int len, b200_cell* out)
 }
 
 extern "C" int b200_diag_get_last_column(b200_handle* h, int i, int len, b200_cell* out) {
-	if (!h || !h->dg.active) return 1;
+	if (!h) return 1;
+	if (!h->dg.active) { h->err = "diag primitive called outside b200_diag_begin/b200_diag_end"; return 1; }
 	auto& d = h->dg;
 	(void)i;
 	if (!out || len < 0 || len > d.bh) { h->err = "b200_diag_get_last_column: bad range"; return 1; }
@@ -674,13 +681,15 @@ extern "C" int b200_diag_get_last_column(b200_handle* h, int i, int len, b200_ce
 }
 
 extern "C" int b200_diag_get_block_scores(b200_handle* h, b200_score* out) {
-	if (!h || !h->dg.active || !out) return 1;
+	if (!h) return 1;
+	if (!h->dg.active || !out) { h->err = "b200_diag_get_block_scores: no open diag session"; return 1; }
 	memcpy(out, h->dg.scores.data(), h->dg.scores.size() * sizeof(b200_score));
 	return 0;
 }
 
 extern "C" int b200_diag_clear_pruned(b200_handle* h, int j0, int j1) {
-	if (!h || !h->dg.active) return 1;
+	if (!h) return 1;
+	if (!h->dg.active) { h->err = "diag primitive called outside b200_diag_begin/b200_diag_end"; return 1; }
 	if (j0 < 0 || j1 > h->n1) { h->err = "b200_diag_clear_pruned: bad range"; return 1; }
 	if (j1 <= j0) return 0;
 	long long n = (long long)j1 - j0;

@@ -1,0 +1,85 @@
+"""End-to-end drop-in parity: build/cudalign (B200Aligner + unmodified MASA-Core stages 1-6) against the parity
+oracle oracle/_ref/oracle_cpu (reference CPUBlockProcessor under the reference's AbstractDiagonalAligner policy)
+on the same FASTA files.  Bit-exact artefacts: crosspoint files of stages 1-4, alignment.00.bin, alignment.00.txt
+(minus the header lines that carry file names), and -- with pruning off -- the stage-1 special-row files."""
+import filecmp
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+import synth  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CUDALIGN = os.path.join(ROOT, "build", "cudalign")
+
+
+def _need_binaries():
+    if not (os.path.exists(CUDALIGN) and O.have_ref_binaries()):
+        pytest.skip("build/cudalign or oracle/_ref binaries not built (need the reference mount at build time)")
+
+
+def _run(exe, fa, fb, wd, extra):
+    cmd = [exe, f"--work-dir={wd}", "--clear", "--verbose=0", *extra, fa, fb]
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+    assert r.returncode == 0, f"{' '.join(cmd)}\n{r.stdout[-3000:]}"
+
+
+def _files(d):
+    out = {}
+    for base, _dirs, names in os.walk(d):
+        for n in names:
+            p = os.path.join(base, n)
+            out[os.path.relpath(p, d)] = p
+    return out
+
+
+def _body(path):
+    return [l for l in open(path) if not (l.startswith("Query: ") or l.startswith("Sbjct: ")) or l[7:20].strip()[:1].isdigit()]
+
+
+def _compare(w_ref, w_new, special_rows):
+    xr, xn = _files(os.path.join(w_ref, "crosspoints")), _files(os.path.join(w_new, "crosspoints"))
+    assert sorted(xr) == sorted(xn), (sorted(xr), sorted(xn))
+    for k in sorted(xr):
+        assert open(xr[k]).read() == open(xn[k]).read(), f"crosspoint file {k} differs"
+    assert filecmp.cmp(os.path.join(w_ref, "alignment.00.bin"), os.path.join(w_new, "alignment.00.bin"), shallow=False), "alignment.00.bin differs"
+    assert _body(os.path.join(w_ref, "alignment.00.txt")) == _body(os.path.join(w_new, "alignment.00.txt")), "alignment.00.txt differs"
+    if special_rows:
+        sr, sn = _files(os.path.join(w_ref, "special_rows", "stage.01.00")), _files(os.path.join(w_new, "special_rows", "stage.01.00"))
+        assert sorted(sr) == sorted(sn), (sorted(sr)[:10], sorted(sn)[:10])
+        for k in sorted(sr):
+            assert filecmp.cmp(sr[k], sn[k], shallow=False), f"special row file {k} differs"
+        return len(sr)
+    return 0
+
+
+CASES = [
+    # name, m, n, homology, extra flags, compare special rows
+    ("sw_3k", 3000, 2700, (500, 2500), [], False),
+    ("sw_40k_nopruning_disk", 40000, 39979, (5000, 35000), ["--no-block-pruning", "--disk-size=4M"], True),
+    ("sw_40k_pruning_ram", 40000, 39979, (5000, 35000), ["--ram-size=3M"], False),
+    ("nw_global_20k", 20000, 21000, (0, 20000), ["--alignment-edges=++", "--disk-size=4M", "--no-block-pruning"], True),
+    ("sw_150k_nopruning", 150000, 140000, (20000, 120000), ["--no-block-pruning", "--disk-size=40M"], True),
+]
+
+
+@pytest.mark.parametrize("name,m,n,hom,extra,sr", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("path", ["fast", "diag"])
+def test_full_pipeline_matches_reference(tmp_path, name, m, n, hom, extra, sr, path):
+    _need_binaries()
+    a, b = synth.make_pair(m, n, [hom], 0.05, 0.02, 0.02, 0, 11)
+    fa, fb = str(tmp_path / "A.fa"), str(tmp_path / "B.fa")
+    synth.write_fasta(fa, a, "A")
+    synth.write_fasta(fb, b, "B")
+    w_ref, w_new = str(tmp_path / "ref"), str(tmp_path / "new")
+    _run(os.path.join(O.REF_DIR, "oracle_cpu"), fa, fb, w_ref, extra)
+    _run(CUDALIGN, fa, fb, w_new, extra + (["--no-fast-path"] if path == "diag" else []))
+    nrows = _compare(w_ref, w_new, sr)
+    if sr:
+        assert nrows > 0
