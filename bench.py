@@ -227,7 +227,7 @@ def main():
     m, n = a.size, b.size
     kern = {"auto": b200.KERNEL_AUTO, "s32": b200.KERNEL_S32, "s16x2": b200.KERNEL_S16X2}[args.kernel]
     al = b200.Aligner(device=local, kernel=kern)
-    j0, j1 = n * rank // world, n * (rank + 1) // world           # column slice of this rank (libmasa.cpp:632-635)
+    j0, j1 = b200.column_slice(n, rank, world)                     # column slice of this rank (libmasa.cpp:632-635)
     if world > 1:
         al.mgpu_setup(dist, rank, world, m)
     al.set_sequences(a, b)                                         # sequences resident in HBM for the `value` leg
@@ -284,7 +284,7 @@ def main():
         total, e2e_total, dev_total = (float(x) for x in t.tolist())
         bests = [None] * world
         dist.all_gather_object(bests, tuple(res["best"]))
-        best = max(bests, key=lambda s: (s[0], -s[1], -s[2]))
+        best = b200.merge_best(bests)
         cells_t = torch.tensor([res["cells"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(cells_t)
         cells = int(cells_t.item())

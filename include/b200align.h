@@ -150,6 +150,12 @@ int b200_mgpu_export(b200_handle* h, int max_rows, b200_ipc_handle* out);
 int b200_mgpu_connect(b200_handle* h, int rank, int world, const b200_ipc_handle* all_handles);
 int b200_mgpu_disconnect(b200_handle* h);
 
+/* Host-side policy helper (no GPU needed): the special-row ids (rows above, relative to i0) that the reference
+ * flushes for a partition of `height` rows: AbstractDiagonalAligner::isSpecialRow,
+ * C/libmasa/aligners/AbstractDiagonalAligner.cpp:466-478 (8192-row floor, top and bottom rows excluded).
+ * Writes at most `cap` ids to `out`, returns the total count. */
+int b200_special_row_ids(int height, int block_height, int interval, int* out, int cap);
+
 /* statistics (IAligner::getProcessedCells etc.) */
 long long b200_processed_cells(const b200_handle* h);
 long long b200_kernel_launches(const b200_handle* h);

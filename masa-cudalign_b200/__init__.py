@@ -62,7 +62,7 @@ EXPORTS = [
     "b200_unset_sequences", "b200_align_partition", "b200_diag_begin", "b200_diag_set_first_row",
     "b200_diag_set_first_column", "b200_diag_process", "b200_diag_get_row", "b200_diag_get_last_column",
     "b200_diag_get_block_scores", "b200_diag_clear_pruned", "b200_diag_end", "b200_match_last_column",
-    "b200_processed_cells", "b200_kernel_launches", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect",
+    "b200_processed_cells", "b200_kernel_launches", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect", "b200_special_row_ids",
 ]
 
 _lib = None
@@ -99,9 +99,34 @@ def load_library(path=None):
     lib.b200_mgpu_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.b200_mgpu_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.b200_mgpu_disconnect.argtypes = [C.c_void_p]
+    lib.b200_special_row_ids.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     if path is None:
         _lib = lib
     return lib
+
+
+def special_row_ids(height, block_height, interval):
+    """Row ids (rows above the special row, relative to the partition) of the reference's flush policy."""
+    lib = load_library()
+    n = lib.b200_special_row_ids(height, block_height, interval, None, 0)
+    out = (C.c_int * max(n, 1))()
+    lib.b200_special_row_ids(height, block_height, interval, out, n)
+    return [out[k] for k in range(n)]
+
+
+def column_slice(n, rank, world):
+    """Columns [j0, j1) owned by `rank` in the chained multi-GPU wavefront: equal weights, the integer arithmetic of
+    the reference's --split/--fork (C/libmasa/libmasa.cpp:632-635)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+def merge_best(bests):
+    """Global best of per-slice bests (score, i, j): highest score, then smallest i, then smallest j
+    (C/common/BestScoreList.hpp:30-38)."""
+    cand = [tuple(b) for b in bests if b is not None and b[1] >= 0]
+    if not cand:
+        return (-INF, -1, -1)
+    return max(cand, key=lambda s: (s[0], -s[1], -s[2]))
 
 
 class B200Error(RuntimeError):

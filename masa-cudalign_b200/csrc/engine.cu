@@ -355,6 +355,13 @@ void special_row_ids(int height, int bh, int interval, std::vector<int>& ids) {
 
 }  // namespace
 
+extern "C" int b200_special_row_ids(int height, int block_height, int interval, int* out, int cap) {
+	std::vector<int> ids;
+	special_row_ids(height, block_height, interval, ids);
+	for (size_t k = 0; k < ids.size() && (int)k < cap && out; k++) out[k] = ids[k];
+	return (int)ids.size();
+}
+
 extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, const b200_callbacks* cb, b200_result* out) {
 	if (!h) return 1;
 	if (!p || !out) { h->err = "b200_align_partition: bad arguments"; return 1; }

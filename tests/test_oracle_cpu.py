@@ -1,0 +1,96 @@
+"""CPU tests (no GPU): pin the plain-C oracle (oracle/gotoh_oracle.c) against the reference.
+
+ * tests/golden/reference_runs.json was produced by the reference's own code (oracle/_ref/oracle_cpu, see
+   tests/golden/make_golden.py): stage-1 best cell and sha256 of every stage-1 special-row file.
+ * when the reference-built binaries are present (build container), the Block-family binary is executed too."""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tools"))
+import synth  # noqa: E402
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_runs.json")))
+
+
+def _pair(g):
+    a, b = synth.make_pair(g["m"], g["n"], [tuple(g["homology"])], g["p_s"], g["p_d"], g["p_i"], 0, g["seed"])
+    return a, b
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_generator_is_reproducible(name):
+    a, b = _pair(GOLD[name]["generator"])
+    assert [hashlib.sha256(a.tobytes()).hexdigest(), hashlib.sha256(b.tobytes()).hexdigest()] == GOLD[name]["seq_sha256"]
+
+
+@pytest.mark.parametrize("name", ["sw_3k", "sw_12k_rows", "sw_40k"])
+def test_sw_best_and_special_rows_match_reference(name):
+    g = GOLD[name]
+    a, b = _pair(g["generator"])
+    ids = sorted(int(os.path.basename(k), 16) for k in g["special_rows_stage1"])
+    o = O.full_matrix(a, b, O.SW, row_ids=[i - 1 for i in ids], want_last_col=False)
+    (_t, i, j, score), = g["crosspoints"]["crosspoint_01.00"]
+    assert o["best"] == (score, i - 1, j - 1)            # crosspoint files are 1-based (AlignerManager.cpp:411-415)
+    for k, meta in g["special_rows_stage1"].items():
+        rid = int(os.path.basename(k), 16)
+        row = o["rows"][rid - 1]
+        assert row.size == meta["cells"]
+        assert [int(row[0]["h"]), int(row[0]["x"])] == meta["first_cell"]
+        assert hashlib.sha256(row.tobytes()).hexdigest() == meta["sha256"], f"{name}: special row {rid:#x}"
+
+
+def test_nw_global_matches_reference():
+    g = GOLD["nw_20k"]
+    a, b = _pair(g["generator"])
+    ids = sorted(int(os.path.basename(k), 16) for k in g["special_rows_stage1"])
+    m, n = a.size, b.size
+    o = O.full_matrix(a, b, O.NW, first_row_type=O.INIT_GAPS, first_col_type=O.INIT_GAPS, row_ids=[i - 1 for i in ids] + [m - 1])
+    (_t, i, j, score), = g["crosspoints"]["crosspoint_01.00"]
+    assert (i, j) == (m, n) and int(o["rows"][m - 1][n]["h"]) == score
+    for k, meta in g["special_rows_stage1"].items():
+        rid = int(os.path.basename(k), 16)
+        assert hashlib.sha256(o["rows"][rid - 1].tobytes()).hexdigest() == meta["sha256"], f"special row {rid:#x}"
+
+
+def test_block_family_binary_agrees(tmp_path):
+    if not O.have_ref_binaries():
+        pytest.skip("oracle/_ref binaries not built")
+    g = GOLD["sw_3k"]
+    a, b = _pair(g["generator"])
+    fa, fb = str(tmp_path / "A.fa"), str(tmp_path / "B.fa")
+    synth.write_fasta(fa, a, "A"); synth.write_fasta(fb, b, "B")
+    wd = O.run_ref("oracle_cpu_block", fa, fb, str(tmp_path / "w"), ["--stage-1", "--no-flush"])
+    pts = O.read_crosspoints(os.path.join(wd, "crosspoints", "crosspoint_01.00"))
+    o = O.full_matrix(a, b, O.SW, want_last_col=False)
+    assert pts == [(0, o["best"][1] + 1, o["best"][2] + 1, o["best"][0])]
+
+
+def test_match_column_rules():
+    # first k wins; match (H+H) before gap (E+E+open) at the same k; overshoot is an error (AlignerUtils.cpp:59-84)
+    buf = np.zeros(6, O.CELL); base = np.zeros(6, O.CELL)
+    buf["h"] = [1, 2, 3, 4, 5, 6]; base["h"] = [0, 0, 0, 6, 0, 4]
+    buf["x"] = -100; base["x"] = -100
+    r = O.match_column(buf, base, 10)
+    assert r == dict(found=True, k=3, score=6, type=0)
+    buf["x"][1] = 3; base["x"][1] = 4                     # 3 + 4 + 3 == 10 at k=1 -> gapped match wins (earlier k)
+    r = O.match_column(buf, base, 10)
+    assert r == dict(found=True, k=1, score=4, type=1)
+    base["h"][0] = 20                                      # overshoot at k=0
+    r = O.match_column(buf, base, 10)
+    assert not r["found"] and r["type"] == -1
+
+
+def test_init_cells():
+    z = O.init_cells(4, O.INIT_ZEROES)
+    assert list(z["h"]) == [0, 0, 0, 0] and set(z["x"]) == {-O.INF}
+    g = O.init_cells(4, O.INIT_GAPS)
+    assert list(g["h"]) == [0, -5, -7, -9]
+    g = O.init_cells(4, O.INIT_GAPS_OPENED)
+    assert list(g["h"]) == [0, -2, -4, -6]
