@@ -174,7 +174,7 @@ class Aligner:
     def align_partition(self, i0=0, j0=0, i1=None, j1=None, recurrence=SMITH_WATERMAN, first_row_init=INIT_ZEROES,
                         first_col_init=INIT_ZEROES, first_row=None, first_col=None, special_row_interval=0,
                         block_height=0, want_special_rows=False, want_last_row=False, want_last_column=False,
-                        want_best_score=True, prune=False, use_callbacks=True, mgpu=False):
+                        want_best_score=True, prune=False, use_callbacks=True, mgpu=False, super_i1=None, super_j1=None):
         """Run b200_align_partition.  first_row / first_col: CELL arrays INCLUDING the corner as element 0
         (n+1 / m+1 cells), used when the init type is INIT_CUSTOM (or to feed gaps through the callback path)."""
         a, b = self._seqs
@@ -184,7 +184,8 @@ class Aligner:
                          first_col_init=first_col_init, special_row_interval=special_row_interval,
                          block_height=block_height, want_special_rows=int(want_special_rows),
                          want_last_row=int(want_last_row), want_last_column=int(want_last_column),
-                         want_best_score=int(want_best_score), prune=int(prune), super_i1=i1, super_j1=j1)
+                         want_best_score=int(want_best_score), prune=int(prune), super_i1=i1 if super_i1 is None else super_i1,
+                         super_j1=j1 if super_j1 is None else super_j1)
         if mgpu:
             part.reserved[0] = 1          # B200_MGPU_CHAIN
         out = {"rows": {}, "row_first": {}, "last_column": [], "scores": []}

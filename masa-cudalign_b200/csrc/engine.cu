@@ -107,6 +107,7 @@ struct b200_handle {
 		const Cell* left = nullptr; Cell* right = nullptr;
 		const int* left_ready = nullptr; int* right_ready = nullptr;
 		int* gbest = nullptr; int* peer_best[8]; int npeer = 0;
+		int prune = 0, prune_i1 = 0, prune_j1 = 0;
 	} ov;
 
 	long long stat_cells = 0;
@@ -209,6 +210,7 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.results = h->results.p;
 	sp.recurrence = recurrence;
 	sp.track = track;
+	sp.prune = h->ov.prune; sp.prune_i1 = h->ov.prune_i1; sp.prune_j1 = h->ov.prune_j1;
 	const bool sw = recurrence == B200_SMITH_WATERMAN;
 	const void* fn = nullptr;
 	if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F) {
@@ -453,6 +455,8 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		}
 	}
 
+	static const bool dbg = getenv("B200_DEBUG") != nullptr;
+	if (dbg) fprintf(stderr, "[b200] launch: %d strips, prune=%d track=%d kind=%d\n", njobs, (int)(p->prune && sw), track, kind);
 	// ---- the alignment itself: one persistent launch
 	if (chain) {
 		Cell* my_cells = reinterpret_cast<Cell*>(h->mg.block + 64);
@@ -466,8 +470,12 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		h->ov.npeer = 0;
 		for (int r = 0; r < h->mg.world; r++) if (r != h->mg.rank) h->ov.peer_best[h->ov.npeer++] = h->mg.peers[r] + 1;
 	}
+	h->ov.prune = (p->prune && sw && track == 2 && kind == B200_KERNEL_S16X2) ? 1 : 0;
+	h->ov.prune_i1 = p->super_i1 > 0 ? p->super_i1 : p->i1;
+	h->ov.prune_j1 = p->super_j1 > 0 ? p->super_j1 : p->j1;
 	CU(h, cudaEventRecord(h->ev0, h->stream));
 	int lrc = launch_strips(h, njobs, p->recurrence, track, kind, SH, true);
+	h->ov.prune = 0;
 	h->ov.left = nullptr; h->ov.right = nullptr; h->ov.left_ready = nullptr; h->ov.right_ready = nullptr; h->ov.gbest = nullptr; h->ov.npeer = 0;
 	if (lrc) return 1;
 	CU(h, cudaEventRecord(h->ev1, h->stream));
@@ -475,6 +483,15 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
 	CU(h, cudaGetLastError());
+	if (dbg) fprintf(stderr, "[b200] kernel done, stop=%d\n", h->hscalars.p[2]);
+	if (dbg && h->hscalars.p[2] != 0) {
+		std::vector<int> prog(njobs);
+		cudaMemcpy(prog.data(), h->progress.p, njobs * sizeof(int), cudaMemcpyDeviceToHost);
+		int shown = 0;
+		for (int k = 0; k < njobs && shown < 12; k++)
+			if (prog[k] < n) { fprintf(stderr, "[b200]   strip %d progress %d / %d (dep progress %d)\n", k, prog[k], n, k ? prog[k - 1] : -1); shown++; }
+	}
+	if (h->hscalars.p[2] != 0) { h->err = "strip kernel watchdog: a border dependency did not advance (code " + std::to_string(h->hscalars.p[2]) + ")"; return 5; }
 	float ms = 0;
 	CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 
@@ -501,6 +518,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		}
 	}
 	out->best = best;
+	if (dbg) fprintf(stderr, "[b200] best %d (%d,%d); dispatching\n", best.score, best.i, best.j);
 
 	// ---- hand the artefacts to the caller in the reference's dispatch format
 	if (have_cb) {
@@ -655,6 +673,7 @@ extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, 
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
 	CU(h, cudaGetLastError());
+	if (h->hscalars.p[2] != 0) { h->err = "strip kernel watchdog: a border dependency did not advance"; return 5; }
 	for (int k = 0; k < njobs; k++) {
 		const Score3& s = h->hresults.p[k];
 		b200_score& o = d.scores[job_bx[k]];

@@ -58,13 +58,15 @@ struct StripParams {
 	Score3* results;        // [njobs] best cell of each job (track != 0)
 	int* global_best;       // running best score of the whole partition (atomicMax)
 	unsigned long long* cells_done;   // statistics
-	const int* stop_flag;   // host-mapped: non-zero asks the kernel to stop claiming jobs
+	int* stop_flag;         // non-zero asks the kernel to stop (set by a spin-wait watchdog: no hung GPU on a protocol bug)
 	const int* left_ready;  // multi-GPU: rows of our left border published by the previous GPU (system scope), or NULL
 	int* right_ready;       // multi-GPU: row counter in the NEXT GPU's exchange block (peer memory), or NULL
 	int* peer_best[8];      // multi-GPU: running-best words of the other GPUs (peer memory)
 	int n_peer_best;
 	int recurrence;         // B200_SMITH_WATERMAN | B200_NEEDLEMAN_WUNSCH
 	int track;              // 0: no best tracking; 1: exact best cell per job; 2: per job, thresholded by global_best
+	int prune;              // SW block pruning inside the strips (needs track == 2)
+	int prune_i1, prune_j1; // end of the (super) partition: bounds of the distance term of the pruning test
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -89,11 +91,27 @@ __device__ __forceinline__ void st_release_sys(int* p, int v) {
 	asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 // wait until the previous GPU has delivered rows [.., upto) of our left border (lane 0 spins, warp follows)
+constexpr unsigned kSpinLimit = 1u << 22;      // each spin costs an L2 round trip (~1 us): a dependency stuck for seconds is a bug
+// spin (lane 0) until the strip above has published `need` columns; the watchdog turns a protocol bug into an error
+__device__ __forceinline__ void wait_progress(const StripParams& p, int dep, int need, int lane) {
+	if (dep < 0) return;
+	if (lane == 0) {
+		unsigned spins = 0;
+		while (ld_acquire(p.progress + dep) < need) {
+			if (ld_relaxed(p.stop_flag)) break;
+			if (++spins > kSpinLimit) { atomicExch(p.stop_flag, 2); break; }
+			__nanosleep(64);
+		}
+	}
+	__syncwarp();
+}
 __device__ __forceinline__ void wait_left(const StripParams& p, int upto, int lane) {
 	if (p.left_ready == nullptr) return;
 	if (lane == 0) {
+		unsigned spins = 0;
 		while (ld_acquire_sys(p.left_ready) < upto) {
 			if (ld_relaxed(p.stop_flag)) break;
+			if (++spins > kSpinLimit) { atomicExch(p.stop_flag, 3); break; }
 			__nanosleep(256);
 		}
 	}
@@ -109,6 +127,14 @@ __device__ __forceinline__ void publish_right(const StripParams& p, int upto, in
 __device__ __forceinline__ void push_best(const StripParams& p, int v) {
 	atomicMax(p.global_best, v);
 	for (int k = 0; k < p.n_peer_best; k++) atomicMax_system(p.peer_best[k], v);
+}
+// Warp-uniform read of a word that other warps/GPUs update concurrently.  After lane-divergent code the lanes
+// of a warp need not be converged, so 32 independent loads could return different values; anything that feeds
+// control flow must be read once and broadcast.
+__device__ __forceinline__ int ld_uniform(const int* p) {
+	__syncwarp();
+	const int v = ld_relaxed(p);
+	return __shfl_sync(0xffffffffu, v, 0);
 }
 __device__ __forceinline__ Cell ldcg_cell(const Cell* p) {
 	int2 v = __ldcg(reinterpret_cast<const int2*>(p));

@@ -22,6 +22,13 @@
 // -INF border inputs (E/F of first row/column, pruned neighbours in SW) are clamped to kNeg and vanish after
 // one cell exactly as -INF does in the reference; NW partitions whose H inputs are -INF take the int32 kernel.
 // Results (bottom row, right column, best cell) are converted back to the reference's exact int32 values.
+//
+// Block pruning (SW stage 1; replaces isBlockPrunable/updatePruningWindow/clearPrunedBlocks,
+// C/libmasa/pruning/AbstractBlockPruning.cpp:70-113, BlockPruningDiagonal.cpp:112-152, on the device):
+// a strip alternates between COMPUTE segments and a SKIP mode, decided every 32 columns.  A 32-column block is
+// skipped when  max(H entering it) + slack + min(rows left, columns left) < best score known so far  (strict,
+// so not even a tie can be lost and the best cell stays exact); skipped cells are published as H = 0 (a valid SW
+// lower bound), which costs one coalesced load, one warp reduction and one store instead of 32 wavefront steps.
 #pragma once
 #include "strip_common.cuh"
 #include "strip_s32.cuh"
@@ -36,6 +43,7 @@ constexpr int kSH16F = 64 * kR16F;
 constexpr int kNeg = -30000;            // local-frame stand-in for -INF
 constexpr int kRebase = 4096;           // re-centre when |reference cell| exceeds this
 constexpr int kCand = 32;               // candidate-ring entries per warp (>= 32: one step can trigger every lane)
+constexpr int kPruneSlack = 66;         // growth possible while the 64-lane pipeline drains, plus rounding
 
 __device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
 __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffffu); }
@@ -73,14 +81,14 @@ struct StripS16 {
 	struct State {
 		unsigned T[R], E[R], sel[R];
 		unsigned tprev, botH, botF, pa, pb;
-		unsigned Zp, thrp;
+		unsigned Zp, thrp, blk;
 		int base;
 		int bs, bi, bj, thr, pub, ncand;
 	};
 
 	template <bool PARTIAL, bool CHECK>
 	__device__ __forceinline__ static void step(const StripParams& p, const StripJob& jb, State& s, Smem& sm, int warp, int lane,
-	                                            int t, int u, int nv_lo, int nv_hi, int vo, int ro) {
+	                                            int t, int u, int nv_lo, int nv_hi, int vo, int ro, int c0, int c1) {
 		const unsigned M2 = dup2(-kGapExt), M5 = dup2(-kGapFirst);
 		unsigned shH = __shfl_up_sync(0xffffffffu, s.botH, 1);
 		unsigned shF = __shfl_up_sync(0xffffffffu, s.botF, 1);
@@ -93,7 +101,7 @@ struct StripS16 {
 		s.pb = s.pa; s.pa = shP;
 		const int col_lo = t - 2 * lane, col_hi = col_lo - 1;
 		bool act = true;
-		if (CHECK) act = (col_lo >= 0) && (col_hi < jb.cols);       // at least one half inside the strip
+		if (CHECK) act = (col_lo >= c0) && (col_hi < c1);           // at least one half inside the segment [c0, c1)
 		bool trig = false, trig_lo = false, trig_hi = false;
 		if (act) {
 			unsigned dT = s.tprev;
@@ -102,8 +110,8 @@ struct StripS16 {
 			// during fill/drain one half may be outside [0, cols): its state must not move
 			unsigned keep = 0;                                        // halves to freeze: 0xffff lo, 0xffff0000 hi
 			if (CHECK) {
-				if (col_lo >= jb.cols) keep |= 0x0000ffffu;
-				if (col_hi < 0) keep |= 0xffff0000u;
+				if (col_lo >= c1) keep |= 0x0000ffffu;
+				if (col_hi < c0) keep |= 0xffff0000u;
 			}
 			s.tprev = CHECK ? ((tup & ~keep) | (s.tprev & keep)) : tup;
 #pragma unroll
@@ -126,7 +134,7 @@ struct StripS16 {
 
 			if (lane == (vo >> 1)) {
 				const int oc = (vo & 1) ? col_hi : col_lo;
-				if (!CHECK || (unsigned)oc < (unsigned)jb.cols) {
+				if (!CHECK || (oc >= c0 && oc < c1)) {
 					int2 o;
 					o.x = (vo & 1) ? hi16(oh) : lo16(oh);
 					o.y = (vo & 1) ? hi16(of) : lo16(of);
@@ -136,7 +144,14 @@ struct StripS16 {
 			if (TRACK) {
 				bool plo, phi;
 				(void)__vibmax_s16x2(smax, s.thrp, &phi, &plo);
-				trig_lo = plo; trig_hi = phi; trig = phi || plo;
+				trig_lo = plo; trig_hi = phi;
+				if (CHECK) {
+					// frozen halves carry stale values: they feed neither the trigger nor the pruning maximum
+					if (keep & 0x0000ffffu) { trig_lo = false; smax = (smax & 0xffff0000u) | 0x8000u; }
+					if (keep & 0xffff0000u) { trig_hi = false; smax = (smax & 0x0000ffffu) | 0x80000000u; }
+				}
+				trig = trig_lo || trig_hi;
+				s.blk = __vmaxs2(s.blk, smax);
 			}
 			if (CHECK && jb.right_off >= 0) {
 				Cell* rb = p.right + jb.right_off;
@@ -161,7 +176,7 @@ struct StripS16 {
 			const unsigned mask = __ballot_sync(0xffffffffu, trig);
 			if (mask) {
 				const int n = __popc(mask);
-				if (s.ncand + n > kCand) drain(jb, s, sm, warp, lane);
+				if (s.ncand + n > kCand) drain(jb, s, sm, warp, lane, c0, c1);
 				if (trig) {
 					const int slot = s.ncand + __popc(mask & ((1u << lane) - 1u));
 					unsigned* e = sm.cand[warp][slot];
@@ -179,7 +194,7 @@ struct StripS16 {
 
 	// Cooperative scan of the candidate ring: lane l examines cell (half = l / R, row = l % R) of every entry.
 	// Takes and returns scalars only, so the register-resident State never has its address taken.
-	__device__ __noinline__ static Best drain_scan(const unsigned (*cand)[R + 2], int ncand, int rows, int cols, int i0, int j0,
+	__device__ __noinline__ static Best drain_scan(const unsigned (*cand)[R + 2], int ncand, int rows, int c0, int c1, int i0, int j0,
 	                                               int base, int lane, Best b) {
 		__syncwarp();
 		const int half = lane / R, r = lane % R;
@@ -190,7 +205,7 @@ struct StripS16 {
 			if (half < 2 && ((meta >> (8 + half)) & 1u)) {
 				const unsigned w = en[r];
 				const int v = 2 * src + half, col = te - v, row = v * R + r;
-				if (row < rows && (unsigned)col < (unsigned)cols) {
+				if (row < rows && col >= c0 && col < c1) {
 					const int hv = (half ? hi16(w) : lo16(w)) + kGapFirst + base;
 					const int i = i0 + row, j = j0 + col;
 					if (better(hv, i, j, b.bs, b.bi, b.bj)) { b.bs = hv; b.bi = i; b.bj = j; }
@@ -201,13 +216,28 @@ struct StripS16 {
 		return b;
 	}
 
-	__device__ __forceinline__ static void drain(const StripJob& jb, State& s, Smem& sm, int warp, int lane) {
+	__device__ __forceinline__ static void drain(const StripJob& jb, State& s, Smem& sm, int warp, int lane, int c0, int c1) {
 		Best b; b.bs = s.bs; b.bi = s.bi; b.bj = s.bj;
-		b = drain_scan(sm.cand[warp], s.ncand, jb.rows, jb.cols, jb.i0, jb.j0, s.base, lane, b);
+		b = drain_scan(sm.cand[warp], s.ncand, jb.rows, c0, c1, jb.i0, jb.j0, s.base, lane, b);
 		s.bs = b.bs; s.bi = b.bi; s.bj = b.bj;
 		s.ncand = 0;
 		const int wb = __reduce_max_sync(0xffffffffu, s.bs);
 		if (wb > s.thr) { s.thr = wb; s.thrp = thr_pack(s.thr, s.base); }
+	}
+
+	// (re)start a compute segment whose left neighbour is all zeros (SW): H = 0, E = -INF
+	__device__ __forceinline__ static void start_zero_segment(State& s, int nv_lo, int nv_hi) {
+		s.base = 0;
+#pragma unroll
+		for (int r = 0; r < R; r++) {
+			s.T[r] = pack2(r < nv_lo ? -kGapFirst : kNeg, r < nv_hi ? -kGapFirst : kNeg);
+			s.E[r] = dup2(kNeg);
+		}
+		s.tprev = dup2(-kGapFirst);
+		s.botH = 0; s.botF = 0; s.pa = 0x02020202u; s.pb = 0x02020202u;
+		s.Zp = 0;
+		s.thrp = thr_pack(s.thr, 0);
+		s.blk = 0x80008000u;
 	}
 
 	template <bool PARTIAL>
@@ -218,12 +248,15 @@ struct StripS16 {
 		int nv_lo = rows - rb_lo; nv_lo = nv_lo < 0 ? 0 : (nv_lo > R ? R : nv_lo);
 		int nv_hi = rows - rb_hi; nv_hi = nv_hi < 0 ? 0 : (nv_hi > R ? R : nv_hi);
 		const int vo = (rows - 1) / R, ro = (rows - 1) % R;
+		const bool lz = (jb.flags & JOB_LEFT_ZERO) != 0;
+		const bool top_minf = (jb.flags & JOB_TOP_MINF) != 0;
+		const bool prune = TRACK && SW && p.prune != 0;
+		const int rows_left = p.prune_i1 - i0;                            // rows from the top of this strip to the end
 
 		State s;
-		if (!(jb.flags & JOB_LEFT_ZERO)) wait_left(p, jb.left_off + rows, lane);
+		if (!lz) wait_left(p, jb.left_off + rows, lane);
 		// ---- left border; the frame starts at the H of the corner
 		const Cell* lb = p.left + jb.left_off;
-		const bool lz = (jb.flags & JOB_LEFT_ZERO) != 0;
 		int base = 0;
 		if (!lz) {
 			int v0 = 0;
@@ -258,93 +291,155 @@ struct StripS16 {
 		s.botH = 0; s.botF = 0; s.pa = 0x02020202u; s.pb = 0x02020202u;
 		s.Zp = dup2(clamp16(-base));
 		s.bs = INT_MIN; s.bi = -1; s.bj = -1; s.thr = INT_MIN; s.pub = INT_MIN; s.thrp = 0x80008000u; s.ncand = 0;
+		s.blk = 0x80008000u;
 
-		int flushed = 0;
-		const int total = cols + V - 1;
-		const bool top_minf = (jb.flags & JOB_TOP_MINF) != 0;
+		int flushed = 0;                       // columns of the bottom row published so far (computed or skipped)
+		int pos = 0;                           // next column to decide in skip mode
+		bool computing = !(prune && lz);       // a zero left border lets the strip start in skip mode
+		long long computed_cols = 0;
+		int bm1 = INT_MIN, bm2 = INT_MIN;      // maxima (true scores) of the last two computed 32-step blocks
 
-#pragma unroll 1
-		for (int tb = 0; tb < total; tb += 32) {
-			// ---- re-centre the frame on H(row 0 of the strip, last column done by virtual lane 0)
-			if (tb > 0 && tb <= cols) {
-				int ref = lo16(s.T[0]) + kGapFirst;
-				ref = __shfl_sync(0xffffffffu, ref, 0);
-				if (ref > kRebase || ref < -kRebase) {
-					const unsigned d = dup2(-ref), fl = dup2(kNeg + (ref > 0 ? ref : 0));
-#pragma unroll
-					for (int r = 0; r < R; r++) {
-						s.T[r] = __vadd2(__vmaxs2(s.T[r], fl), d);
-						s.E[r] = __vadd2(__vmaxs2(s.E[r], fl), d);
-					}
-					s.tprev = __vadd2(__vmaxs2(s.tprev, fl), d);
-					s.botH = __vadd2(__vmaxs2(s.botH, fl), d);
-					s.botF = __vadd2(__vmaxs2(s.botF, fl), d);
-					s.base += ref;
-					s.Zp = dup2(clamp16(-s.base));
-					s.thrp = thr_pack(s.thr, s.base);
+		for (;;) {
+			if (!computing) {
+				// =========================== SKIP mode: one 32-column block per iteration ===========================
+				if (pos >= cols) break;
+				const int need = pos + 32 < cols ? pos + 32 : cols;
+				wait_progress(p, jb.dep, need, lane);
+				if (p.track == 2) {
+					const int g = ld_uniform(p.global_best);
+					if (g > s.thr) { s.thr = g; s.pub = g; }
 				}
-			}
-			// ---- stage the next 32 columns of top border and seq1 (coalesced), gated on the strip above
-			if (tb < cols) {
-				const int need = tb + 32 < cols ? tb + 32 : cols;
-				if (jb.dep >= 0) {
-					if (lane == 0) {
-						while (ld_acquire(p.progress + jb.dep) < need) {
-							if (ld_relaxed(p.stop_flag)) break;
-							__nanosleep(64);
-						}
+				const int c = pos + lane;
+				int th = 0;
+				if (c < need && !top_minf) th = __ldcg(&p.busH[j0 + c].h);
+				int tmax = __reduce_max_sync(0xffffffffu, th);
+				if (tmax < 0) tmax = 0;
+				const int cols_left = p.prune_j1 - (j0 + pos);
+				const long long bound = (long long)tmax + kPruneSlack + (rows_left < cols_left ? rows_left : cols_left);
+				if (s.thr != INT_MIN && bound < (long long)s.thr) {
+					if (c < need) {
+						stcg_cell(p.busH + j0 + c, 0, -kInf);
+						if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, 0, -kInf);
 					}
+					pos = need; flushed = need;
 					__syncwarp();
+					if (lane == 0) { __threadfence(); st_release(p.progress + job, flushed); }
+					continue;
 				}
-				const int c = tb + lane;
-				int th = kNeg, tf = kNeg; unsigned pw = 0x02020202u;
-				if (c < cols) {
-					if (!top_minf) {
-						const Cell tv = ldcg_cell(p.busH + j0 + c);
-						th = tv.h < -kInf / 2 ? kNeg : clamp16(tv.h - s.base);
-						tf = tv.x < -kInf / 2 ? kNeg : clamp16(tv.x - s.base);
+				start_zero_segment(s, nv_lo, nv_hi);
+				computing = true;
+				bm1 = bm2 = INT_MIN;
+			}
+
+			// =========================== COMPUTE mode: one segment [c0, c1) ===========================
+			const int c0 = pos;
+			int c1 = cols;
+#pragma unroll 1
+			for (int tb = c0; tb < c1 + V - 1; tb += 32) {
+				// ---- re-centre the frame on H(row 0 of the strip, last column done by virtual lane 0)
+				if (tb > c0 && tb <= c1) {
+					int ref = lo16(s.T[0]) + kGapFirst;
+					ref = __shfl_sync(0xffffffffu, ref, 0);
+					if (ref > kRebase || ref < -kRebase) {
+						const unsigned d = dup2(-ref), fl = dup2(kNeg + (ref > 0 ? ref : 0));
+#pragma unroll
+						for (int r = 0; r < R; r++) {
+							s.T[r] = __vadd2(__vmaxs2(s.T[r], fl), d);
+							s.E[r] = __vadd2(__vmaxs2(s.E[r], fl), d);
+						}
+						s.tprev = __vadd2(__vmaxs2(s.tprev, fl), d);
+						s.botH = __vadd2(__vmaxs2(s.botH, fl), d);
+						s.botF = __vadd2(__vmaxs2(s.botF, fl), d);
+						s.base += ref;
+						s.Zp = dup2(clamp16(-s.base));
+						s.thrp = thr_pack(s.thr, s.base);
 					}
-					const int k = code_of(p.s1[j0 + c]);
-					pw = 0x02020202u ^ (0x04u << (8 * k));      // byte k = 6 (match+5), others 2 (mismatch+5)
 				}
-				sm.top[warp][lane] = make_int2((int)((unsigned)th << 16), (int)((unsigned)tf << 16));
-				sm.prof[warp][lane] = pw;
-				if (TRACK && p.track == 2) {
-					// share the running best: publish ours, adopt a higher one (monotone, staleness is harmless)
-					if (s.thr > s.pub) { if (lane == 0) push_best(p, s.thr); s.pub = s.thr; }
-					const int g = ld_relaxed(p.global_best);
-					if (g > s.thr) { s.thr = g; s.pub = g; s.thrp = thr_pack(s.thr, s.base); }
+				// ---- stage the next 32 columns of top border and seq1 (coalesced), gated on the strip above
+				if (tb < c1) {
+					const int need = tb + 32 < cols ? tb + 32 : cols;
+					wait_progress(p, jb.dep, need, lane);
+					if (TRACK && p.track == 2) {
+						// share the running best: publish ours, adopt a higher one (monotone, staleness is harmless)
+						if (s.thr > s.pub) { if (lane == 0) push_best(p, s.thr); s.pub = s.thr; }
+						const int g = ld_uniform(p.global_best);
+						if (g > s.thr) { s.thr = g; s.pub = g; s.thrp = thr_pack(s.thr, s.base); }
+					}
+					const int c = tb + lane;
+					Cell tv; tv.h = -kInf; tv.x = -kInf;
+					if (c < cols && !top_minf) tv = ldcg_cell(p.busH + j0 + c);
+					if (prune && tb > c0) {
+						// stop the segment here if nothing entering [tb, ...) can still reach the best known score
+						int tmax = __reduce_max_sync(0xffffffffu, c < cols ? tv.h : 0);
+						if (tmax < 0) tmax = 0;
+						int in_max = tmax > bm1 ? tmax : bm1;
+						in_max = in_max > bm2 ? in_max : bm2;
+						const int cols_left = p.prune_j1 - (j0 + tb);
+						const long long bound = (long long)in_max + kPruneSlack + (rows_left < cols_left ? rows_left : cols_left);
+						if (s.thr != INT_MIN && bm1 != INT_MIN && bound < (long long)s.thr) c1 = tb;
+					}
+					if (tb < c1) {
+						int th = kNeg, tf = kNeg; unsigned pw = 0x02020202u;
+						if (c < cols) {
+							th = tv.h < -kInf / 2 ? kNeg : clamp16(tv.h - s.base);
+							tf = tv.x < -kInf / 2 ? kNeg : clamp16(tv.x - s.base);
+							const int k = code_of(p.s1[j0 + c]);
+							pw = 0x02020202u ^ (0x04u << (8 * k));      // byte k = 6 (match+5), others 2 (mismatch+5)
+						}
+						sm.top[warp][lane] = make_int2((int)((unsigned)th << 16), (int)((unsigned)tf << 16));
+						sm.prof[warp][lane] = pw;
+						__syncwarp();
+					}
 				}
-				__syncwarp();
-			}
 
-			// ---- 32 steps; the check-free body runs whenever every virtual lane is inside [0, cols)
-			const bool steady = (tb >= V) && (tb + 32 < cols);
-			if (steady) {
+				// ---- 32 steps; the check-free body runs whenever every virtual lane is inside [c0, c1)
+				const bool steady = (tb >= c0 + V) && (tb + 32 < c1);
+				if (steady) {
 #pragma unroll 1
-				for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro);
-			} else {
+					for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
+				} else {
 #pragma unroll 1
-				for (int u = 0; u < 32; u++) step<PARTIAL, true>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro);
-			}
-
-			if (TRACK && s.ncand > 0) drain(jb, s, sm, warp, lane);
-
-			// ---- publish the columns of the bottom row completed during these 32 steps (exact int32 values)
-			int cdone = tb + 31 - vo; cdone = cdone < cols - 1 ? cdone : cols - 1;
-			if (cdone >= flushed) {
-				__syncwarp();
-				for (int c = flushed + lane; c <= cdone; c += 32) {
-					const int2 v = sm.bot[warp][c & 63];
-					const int hv = v.x <= kNeg ? -kInf : v.x + s.base, fv = v.y <= kNeg ? -kInf : v.y + s.base;
-					stcg_cell(p.busH + j0 + c, hv, fv);
-					if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, hv, fv);
+					for (int u = 0; u < 32; u++) step<PARTIAL, true>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
 				}
-				flushed = cdone + 1;
-				if (flushed == cols && jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
-				__syncwarp();
-				if (lane == 0) { __threadfence(); st_release(p.progress + job, flushed); }
+				if (TRACK) {
+					if (s.ncand > 0) drain(jb, s, sm, warp, lane, c0, c1);
+					if (prune) {
+						const int lm = lo16(s.blk) > hi16(s.blk) ? lo16(s.blk) : hi16(s.blk);
+						const int bm = __reduce_max_sync(0xffffffffu, lm);
+						bm2 = bm1;
+						bm1 = bm <= -32768 ? 0 : bm + s.base;
+						s.blk = 0x80008000u;
+					}
+				}
+
+				// ---- publish the columns of the bottom row completed during these 32 steps (exact int32 values)
+				int cdone = tb + 31 - vo; cdone = cdone < c1 - 1 ? cdone : c1 - 1;
+				if (cdone >= flushed) {
+					__syncwarp();
+					for (int c = flushed + lane; c <= cdone; c += 32) {
+						const int2 v = sm.bot[warp][c & 63];
+						const int hv = v.x <= kNeg ? -kInf : v.x + s.base, fv = v.y <= kNeg ? -kInf : v.y + s.base;
+						stcg_cell(p.busH + j0 + c, hv, fv);
+						if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, hv, fv);
+					}
+					flushed = cdone + 1;
+					if (flushed == cols && jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
+					__syncwarp();
+					if (lane == 0) { __threadfence(); st_release(p.progress + job, flushed); }
+				}
 			}
+			computed_cols += c1 - c0;
+			if (c1 >= cols) break;
+			pos = c1;                          // the segment was cut short: continue in skip mode
+			computing = false;
+		}
+
+		if (prune && !computing && jb.right_off >= 0) {
+			// the strip ended in skip mode: its right border is the zero border
+			Cell* rb = p.right + jb.right_off;
+			for (int k = lane; k < rows; k += 32) stcg_cell(rb + 1 + k, 0, -kInf);
+			if (lane == 0) __stcg(&rb[0].h, 0);
+			publish_right(p, jb.left_off + rows, lane);
 		}
 
 		if (TRACK) {
@@ -362,7 +457,7 @@ struct StripS16 {
 				if (bs != INT_MIN) push_best(p, bs);
 			}
 		}
-		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)cols);
+		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)computed_cols);
 	}
 };
 
@@ -376,7 +471,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 12) strip_kernel_s16(cons
 		if (lane == 0) job = atomicAdd(p.job_counter, 1);
 		job = __shfl_sync(0xffffffffu, job, 0);
 		if (job >= p.njobs) break;
-		if (ld_relaxed(p.stop_flag)) break;
+		if (ld_uniform(p.stop_flag)) break;
 		const int flags = p.jobs[job].flags, rows = p.jobs[job].rows;
 		if (flags & JOB_PRUNED) {
 			// same semantics as the int32 kernel: -INF to the right border, no score (CUDAligner.cu:950-960)

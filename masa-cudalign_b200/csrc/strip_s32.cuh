@@ -77,15 +77,7 @@ struct StripS32 {
 			// ---- stage the next 32 columns of top border and seq1 (coalesced), gated on the strip above
 			if (tb < cols) {
 				int need = tb + 32 < cols ? tb + 32 : cols;
-				if (jb.dep >= 0) {
-					if (lane == 0) {
-						while (ld_acquire(p.progress + jb.dep) < need) {
-							if (ld_relaxed(p.stop_flag)) break;
-							__nanosleep(64);
-						}
-					}
-					__syncwarp();
-				}
+				wait_progress(p, jb.dep, need, lane);
 				int c = tb + lane;
 				Cell tv; tv.h = -kInf; tv.x = -kInf; unsigned char ch = 0;
 				if (c < cols) {
@@ -96,7 +88,7 @@ struct StripS32 {
 				sm.seq[warp][lane] = ch;
 				if (TRACK && p.track == 2) {
 					if (thr > pub) { if (lane == 0) push_best(p, thr); pub = thr; }
-					const int g = ld_relaxed(p.global_best);
+					const int g = ld_uniform(p.global_best);
 					if (g > thr) { thr = g; pub = g; }
 				}
 				__syncwarp();
@@ -207,7 +199,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) strip_kernel_s32(const St
 		if (lane == 0) job = atomicAdd(p.job_counter, 1);
 		job = __shfl_sync(0xffffffffu, job, 0);
 		if (job >= p.njobs) break;
-		if (ld_relaxed(p.stop_flag)) break;
+		if (ld_uniform(p.stop_flag)) break;
 		K::run_job(p, job, sm, warp, lane);
 	}
 }

@@ -87,3 +87,25 @@ def test_custom_borders_subpartition(b200):
         assert np.array_equal(r["last_column"][1:], o["last_col"][1:])
         assert r["best"] == (o["best"][0], o["best"][1] + i0, o["best"][2] + j0)
         al.close()
+
+
+@pytest.mark.parametrize("m,n,hom", [(60000, 50000, (5000, 45000)), (30000, 90000, (1000, 29000)), (150000, 150000, (20000, 130000)), (20000, 20000, (0, 0))])
+def test_pruning_keeps_best_exact(b200, m, n, hom):
+    """On-device block pruning (SW): the best cell must stay bit-exact, cells are skipped, and every published
+    bottom-row cell is a lower bound of the exact one (skipped cells are published as H = 0)."""
+    a, b = synth.make_pair(m, n, [hom], 0.05, 0.01, 0.01, 0, 5)
+    al = b200.Aligner(kernel=b200.KERNEL_S16X2)
+    al.set_sequences(a, b)
+    exact = al.align_partition(want_last_row=True, want_last_column=True, prune=False)
+    r = al.align_partition(want_last_row=True, want_last_column=True, prune=True)
+    assert r["best"] == exact["best"]
+    assert r["cells"] <= exact["cells"]
+    if hom[1] - hom[0] > 20000:
+        assert r["cells"] < 0.9 * exact["cells"], "a long planted alignment must let the strips skip blocks"
+    assert np.all(r["rows"][m]["h"][1:] <= exact["rows"][m]["h"][1:])
+    assert np.all(r["last_column"]["h"][1:] <= exact["last_column"]["h"][1:])
+    assert np.all(r["rows"][m]["h"][1:] >= 0)
+    if m * n <= 4_000_000_000:
+        o = O.full_matrix(a, b, O.SW, want_last_col=False)
+        assert r["best"] == o["best"]
+    al.close()
