@@ -177,7 +177,8 @@ int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 	int lim = per_sm * kWarpsPerBlock;
 	if (h->cfg.warps_per_sm > 0) lim = std::min(lim, h->cfg.warps_per_sm);
 	int best_w = lim;
-	if (h->cfg.warps_per_sm <= 0 && chained && njobs > h->sm_count * kSatWarps) {
+	// with pruning about half of the resident strips are skipping (and mostly sleeping): keep every slot occupied
+	if (h->cfg.warps_per_sm <= 0 && chained && !h->ov.prune && njobs > h->sm_count * kSatWarps) {
 		double best_cost = 1e300;
 		for (int w = std::min(kSatWarps, lim); w <= lim; w++) {
 			long long cap = (long long)h->sm_count * w;

@@ -71,9 +71,10 @@ struct StripS16 {
 	static constexpr int SH = V * R;
 
 	struct Smem {
-		int2 top[kWarpsPerBlock][32];        // {H<<16, F<<16} of the top border in the local frame
+		unsigned topH[kWarpsPerBlock][32];   // H<<16 of the top border in the local frame (lane 0 injects it into its low half)
+		unsigned topF[kWarpsPerBlock][32];   // F<<16
 		unsigned prof[kWarpsPerBlock][32];   // column profile words: byte k = s(k, column base) + 5
-		int2 bot[kWarpsPerBlock][64];        // local (H,F) of the strip's bottom row, ring over columns
+		uint2 bot[kWarpsPerBlock][64];       // packed (H,F) registers of the lane that owns the bottom row, ring over columns
 		unsigned cand[kWarpsPerBlock][kCand][R + 2];   // deferred best-cell candidates: T[0..R) of a lane + {step, lane|halves<<8}
 	};
 
@@ -93,9 +94,7 @@ struct StripS16 {
 		unsigned shH = __shfl_up_sync(0xffffffffu, s.botH, 1);
 		unsigned shF = __shfl_up_sync(0xffffffffu, s.botF, 1);
 		unsigned shP = __shfl_up_sync(0xffffffffu, s.pb, 1);
-		const int2 tv = sm.top[warp][u];
-		const unsigned tp = sm.prof[warp][u];
-		if (lane == 0) { shH = (unsigned)tv.x; shF = (unsigned)tv.y; shP = tp; }
+		if (lane == 0) { shH = sm.topH[warp][u]; shF = sm.topF[warp][u]; shP = sm.prof[warp][u]; }   // predicated LDS, no SEL
 		const unsigned upH = prmt(shH, s.botH, 0x5432);      // lo <- neighbour's hi, hi <- own lo
 		const unsigned upF = prmt(shF, s.botF, 0x5432);
 		s.pb = s.pa; s.pa = shP;
@@ -134,12 +133,7 @@ struct StripS16 {
 
 			if (lane == (vo >> 1)) {
 				const int oc = (vo & 1) ? col_hi : col_lo;
-				if (!CHECK || (oc >= c0 && oc < c1)) {
-					int2 o;
-					o.x = (vo & 1) ? hi16(oh) : lo16(oh);
-					o.y = (vo & 1) ? hi16(of) : lo16(of);
-					sm.bot[warp][oc & 63] = o;
-				}
+				if (!CHECK || (oc >= c0 && oc < c1)) sm.bot[warp][oc & 63] = make_uint2(oh, of);   // halves are picked at flush time
 			}
 			if (TRACK) {
 				bool plo, phi;
@@ -386,7 +380,8 @@ struct StripS16 {
 							const int k = code_of(p.s1[j0 + c]);
 							pw = 0x02020202u ^ (0x04u << (8 * k));      // byte k = 6 (match+5), others 2 (mismatch+5)
 						}
-						sm.top[warp][lane] = make_int2((int)((unsigned)th << 16), (int)((unsigned)tf << 16));
+						sm.topH[warp][lane] = (unsigned)th << 16;
+						sm.topF[warp][lane] = (unsigned)tf << 16;
 						sm.prof[warp][lane] = pw;
 						__syncwarp();
 					}
@@ -417,8 +412,9 @@ struct StripS16 {
 				if (cdone >= flushed) {
 					__syncwarp();
 					for (int c = flushed + lane; c <= cdone; c += 32) {
-						const int2 v = sm.bot[warp][c & 63];
-						const int hv = v.x <= kNeg ? -kInf : v.x + s.base, fv = v.y <= kNeg ? -kInf : v.y + s.base;
+						const uint2 pv = sm.bot[warp][c & 63];
+						const int vx = (vo & 1) ? hi16(pv.x) : lo16(pv.x), vy = (vo & 1) ? hi16(pv.y) : lo16(pv.y);
+						const int hv = vx <= kNeg ? -kInf : vx + s.base, fv = vy <= kNeg ? -kInf : vy + s.base;
 						stcg_cell(p.busH + j0 + c, hv, fv);
 						if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, hv, fv);
 					}
