@@ -150,6 +150,19 @@ int b200_mgpu_export(b200_handle* h, int max_rows, b200_ipc_handle* out);
 int b200_mgpu_connect(b200_handle* h, int rank, int world, const b200_ipc_handle* all_handles);
 int b200_mgpu_disconnect(b200_handle* h);
 
+/* Stage 4: batched Myers-Miller partition split on the GPU (replaces reduce_partitions/split_thread/ort_split_2 of
+ * C/stage4/sw_stage4.cpp:87-380,806-852, 4 pthreads in the reference).  Crosspoints are the reference's
+ * crosspoint_t (C/common/Crosspoint.hpp:30-40): 0-based prefix lengths (i, j), type 0 MATCH / 1 GAP_1 / 2 GAP_2.
+ * The sequences are the ones given to b200_set_sequences (whole trimmed sequences, like stage 4's
+ * seq->getData()).  Only the default OPTIMIZED strategy (ort_split_2) is implemented.
+ *   b200_stage4_round : one round; out[k] (k = 1..n-1) = midpoint of partition (k-1, k) or type = -1 (not split)
+ *   b200_stage4       : rounds + merge_partitions (:785-804) until the largest partition <= max_partition
+ *                       (:926-945); writes at most cap crosspoints, *n_out = count.
+ * Return 6 = the reference's fatal conditions ("Error Match" / "NOT FOUND"). */
+typedef struct { int i; int j; int type; int score; } b200_xpoint;
+int b200_stage4_round(b200_handle* h, const b200_xpoint* in, int n, int max_partition, b200_xpoint* out);
+int b200_stage4(b200_handle* h, const b200_xpoint* in, int n, int max_partition, b200_xpoint* out, int cap, int* n_out);
+
 /* Host-side policy helper (no GPU needed): the special-row ids (rows above, relative to i0) that the reference
  * flushes for a partition of `height` rows: AbstractDiagonalAligner::isSpecialRow,
  * C/libmasa/aligners/AbstractDiagonalAligner.cpp:466-478 (8192-row floor, top and bottom rows excluded).

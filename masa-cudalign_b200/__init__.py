@@ -19,6 +19,7 @@ INIT_ZEROES, INIT_GAPS, INIT_GAPS_OPENED, INIT_CUSTOM = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_S32, KERNEL_S16X2 = 0, 1, 2
 
 CELL = np.dtype([("h", "<i4"), ("x", "<i4")])
+XPOINT = np.dtype([("i", "<i4"), ("j", "<i4"), ("type", "<i4"), ("score", "<i4")])      # == crosspoint_t
 
 
 class Config(C.Structure):
@@ -62,7 +63,7 @@ EXPORTS = [
     "b200_unset_sequences", "b200_align_partition", "b200_diag_begin", "b200_diag_set_first_row",
     "b200_diag_set_first_column", "b200_diag_process", "b200_diag_get_row", "b200_diag_get_last_column",
     "b200_diag_get_block_scores", "b200_diag_clear_pruned", "b200_diag_end", "b200_match_last_column",
-    "b200_processed_cells", "b200_kernel_launches", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect", "b200_special_row_ids",
+    "b200_processed_cells", "b200_kernel_launches", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect", "b200_special_row_ids", "b200_stage4_round", "b200_stage4",
 ]
 
 _lib = None
@@ -100,6 +101,8 @@ def load_library(path=None):
     lib.b200_mgpu_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.b200_mgpu_disconnect.argtypes = [C.c_void_p]
     lib.b200_special_row_ids.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.b200_stage4_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.b200_stage4.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     if path is None:
         _lib = lib
     return lib
@@ -292,6 +295,23 @@ class Aligner:
         m = Match()
         self._check(self.lib.b200_match_last_column(self.h, bu.ctypes.data, ba.ctypes.data, bu.size, goal, C.byref(m)), "b200_match_last_column")
         return dict(found=bool(m.found), k=m.k, score=m.score, type=m.type)
+
+    # ---- stage 4 ---------------------------------------------------------------------------------------
+    def stage4_round(self, points, max_partition=16):
+        """One batched split round: returns XPOINT[n]; entry k is the midpoint of partition (k-1, k), type -1 = none."""
+        pts = np.ascontiguousarray(points, dtype=XPOINT)
+        out = np.zeros(pts.size, XPOINT)
+        self._check(self.lib.b200_stage4_round(self.h, pts.ctypes.data, pts.size, max_partition, out.ctypes.data), "b200_stage4_round")
+        return out
+
+    def stage4(self, points, max_partition=16):
+        """All rounds + merges until the largest partition is <= max_partition (the reference's stage 4)."""
+        pts = np.ascontiguousarray(points, dtype=XPOINT)
+        cap = max(4 * (int(pts["i"].max() - pts["i"].min()) + int(pts["j"].max() - pts["j"].min())) + 64, 4 * pts.size)
+        out = np.zeros(cap, XPOINT)
+        n_out = C.c_int()
+        self._check(self.lib.b200_stage4(self.h, pts.ctypes.data, pts.size, max_partition, out.ctypes.data, cap, C.byref(n_out)), "b200_stage4")
+        return out[:n_out.value].copy()
 
     def processed_cells(self):
         return self.lib.b200_processed_cells(self.h)

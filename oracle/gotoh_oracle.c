@@ -99,3 +99,119 @@ int go_block_prunable(int score, int best, int i0, int j0, int i1, int j1, int m
     }
     return (score + inc) <= best;
 }
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Stage 4 restatement (C/stage4/sw_stage4.cpp)
+ * ---------------------------------------------------------------------------------------------------------- */
+#define GAP_FIRST (GAP_OPEN + GAP_EXT)
+#define T_MATCH 0
+#define T_GAP_1 1
+#define T_GAP_2 2
+#define MAX3(a, b, c) (MAX2(MAX2((a), (b)), (c)))
+
+/* one column of the half-matrix: sw_stage4.cpp:254-273 (processCol); s0 is indexed with stride (reverse = -1) */
+static go_cell s4_process_col(const unsigned char* s0, int stride, unsigned char c, int h11, int h10, go_cell* col, int len) {
+    int f0 = -GO_INF;
+    for (int j = 0; j < len; j++) {
+        col[j].x = MAX2(col[j].h - GAP_FIRST, col[j].x - GAP_EXT);
+        f0 = MAX2(h10 - GAP_FIRST, f0 - GAP_EXT);
+        h10 = MAX3(h11 + ((c == s0[(long)j * stride]) ? MATCH : MISMATCH), col[j].x, f0);
+        h11 = col[j].h;
+        col[j].h = h10;
+    }
+    go_cell r; r.x = f0; r.h = h10;
+    return r;
+}
+
+/* sw_stage4.cpp:275-294 (match): 1 = found, 0 = not yet, -1 = "Error Match" */
+static int s4_match(go_cell a, go_cell b, int diff, go_xpoint* pt) {
+    int sum_match = a.h + b.h, sum_gap = a.x + b.x + GAP_OPEN;
+    if (sum_match == diff) { pt->type = T_MATCH; pt->score = a.h; return 1; }
+    if (sum_gap == diff) { pt->type = T_GAP_2; pt->score = a.x; return 1; }
+    if (sum_match > diff || sum_gap > diff) return -1;
+    return 0;
+}
+
+/* ort_split_2, sw_stage4.cpp:297-380.  s0/s1 are accessed through (base, stride) so that the transposed call of
+ * split_thread (seq1 as rows) and the reversed halves need no copies. */
+static int s4_ort_split_2(const unsigned char* q0, const unsigned char* q1, int i0, int j0, int i1, int j1,
+                          int type_s, int type_e, int score_s, int score_e, go_xpoint* cross) {
+    int len0 = i1 - i0, len1 = j1 - j0;
+    int diff = score_e - score_s;
+    int imid0 = len0 / 2, imid1 = len0 - imid0;
+    int jmid1 = len1 - len1 / 2;
+    go_cell* c0 = (go_cell*)malloc(sizeof(go_cell) * (size_t)(imid0 + 1));
+    go_cell* c1 = (go_cell*)malloc(sizeof(go_cell) * (size_t)(imid1 + 1));
+    go_cell* r0 = (go_cell*)malloc(sizeof(go_cell) * (size_t)(jmid1 + 2));
+    go_cell* r1 = (go_cell*)malloc(sizeof(go_cell) * (size_t)(jmid1 + 2));
+    for (int i = 0; i < imid0; i++) { c0[i].h = -(i + 1) * GAP_EXT - GAP_OPEN * (type_s != T_GAP_2); c0[i].x = -GO_INF; }
+    for (int i = 0; i < imid1; i++) { c1[i].h = -(i + 1) * GAP_EXT - GAP_OPEN; c1[i].x = -GO_INF; }
+    r0[0].h = r0[0].x = c0[imid0 - 1].h;
+    r1[0].h = r1[0].x = c1[imid1 - 1].h;
+    int d0 = (type_s != T_MATCH) ? -GO_INF : 0, d1 = (type_e != T_MATCH) ? -GO_INF : 0;
+    int rc = -2;   /* NOT FOUND */
+    for (int j = 0; j < len1; j++) {
+        int h0 = -(j + 1) * GAP_EXT - GAP_OPEN * (type_s != T_GAP_1);
+        go_cell rr0 = s4_process_col(q0 + i0, 1, q1[j0 + j], d0, h0, c0, imid0);
+        d0 = h0;
+        int h1 = -(j + 1) * GAP_EXT - GAP_OPEN;
+        go_cell rr1 = s4_process_col(q0 + i1 - 1, -1, q1[j1 - 1 - j], d1, h1, c1, imid1);
+        d1 = h1;
+        if (j + 1 <= jmid1) { r0[j + 1] = rr0; r1[j + 1] = rr1; }
+        if (j + 1 >= jmid1) {
+            int m = s4_match(rr0, r1[len1 - (j + 1)], diff, cross);
+            if (m < 0) { rc = -1; break; }
+            if (m) { cross->j = j0 + (j + 1); cross->i = imid0 + i0; cross->score += score_s; rc = 0; break; }
+            m = s4_match(r0[len1 - (j + 1)], rr1, diff, cross);
+            if (m < 0) { rc = -1; break; }
+            if (m) { cross->j = j0 + (len1 - (j + 1)); cross->i = imid0 + i0; cross->score += score_s; rc = 0; break; }
+        }
+    }
+    free(c0); free(c1); free(r0); free(r1);
+    return rc;
+}
+
+int go_stage4_split_one(const unsigned char* seq0, const unsigned char* seq1, go_xpoint a, go_xpoint b, int max_part, go_xpoint* out) {
+    static const int inv_type[3] = {0, 2, 1};
+    int di = b.i - a.i, dj = b.j - a.j;
+    out->type = -1; out->i = out->j = out->score = 0;
+    if (di == 0 || dj == 0) return 0;
+    if (di < dj) {                                   /* transposed: sw_stage4.cpp:135-171 */
+        if (!(a.j < b.j - max_part)) return 0;
+        go_xpoint t;
+        int rc = s4_ort_split_2(seq1, seq0, a.j, a.i, b.j, b.i, inv_type[a.type], inv_type[b.type], a.score, b.score, &t);
+        if (rc) return rc;
+        out->i = t.j; out->j = t.i; out->type = inv_type[t.type]; out->score = t.score;
+    } else {
+        if (!(a.i < b.i - max_part)) return 0;
+        go_xpoint t;
+        int rc = s4_ort_split_2(seq0, seq1, a.i, a.j, b.i, b.j, a.type, b.type, a.score, b.score, &t);
+        if (rc) return rc;
+        *out = t;
+    }
+    return 0;
+}
+
+int go_stage4_round(const unsigned char* seq0, const unsigned char* seq1, const go_xpoint* in, int n, int max_part, go_xpoint* out, int* changed) {
+    int cnt = 0;
+    *changed = 0;
+    out[cnt++] = in[0];
+    for (int k = 1; k < n; k++) {
+        go_xpoint np;
+        int rc = go_stage4_split_one(seq0, seq1, in[k - 1], in[k], max_part, &np);
+        if (rc) return rc;
+        int diff_pos = (np.i != in[k - 1].i || np.j != in[k - 1].j);     /* merge_partitions, :785-804 */
+        if (np.type != -1 && diff_pos) { *changed = 1; out[cnt++] = np; }
+        out[cnt++] = in[k];
+    }
+    return cnt;
+}
+
+int go_largest_partition(const go_xpoint* pts, int n) {                 /* CrosspointsFile.cpp:71-92 */
+    int mi = 0, mj = 0;
+    for (int k = 1; k < n; k++) {
+        int di = abs(pts[k - 1].i - pts[k].i), dj = abs(pts[k - 1].j - pts[k].j);
+        if (di != 0 && dj != 0) { if (mi < di) mi = di; if (mj < dj) mj = dj; }
+    }
+    return mi > mj ? mi : mj;
+}

@@ -8,7 +8,7 @@ extern "C" {
 typedef struct { int h; int x; } go_cell;          /* x = F for row cells, E for column cells (libmasaTypes.hpp:35-41) */
 typedef struct { int score, i, j; } go_score;      /* 0-based cell indices (libmasaTypes.hpp:88-95) */
 typedef struct { int found, k, score, type; } go_match;   /* libmasaTypes.hpp:51-60 */
-typedef struct { int type, i, j, score; } go_xpoint;      /* common/Crosspoint.hpp */
+typedef struct { int i, j, type, score; } go_xpoint;      /* == crosspoint_t, common/Crosspoint.hpp:30-40 */
 
 #define GO_INF 999999999
 #define GO_SW 1   /* SMITH_WATERMAN  (libmasa/IManager.hpp) */
@@ -31,6 +31,16 @@ void go_init_cells(go_cell* buf, int len, int type, int start_pos);
 go_match go_match_column(const go_cell* buffer, const go_cell* base, int len, int goal, int gap_open);
 
 int go_block_prunable(int score, int best, int i0, int j0, int i1, int j1, int max_i, int max_j, int recurrence);
+
+/* Stage 4 (C/stage4/sw_stage4.cpp): Myers-Miller midpoint of one partition with the default OPTIMIZED strategy
+ * (ort_split_2, :297-380) and the per-partition driver logic of split_thread (:87-217).  Crosspoints carry
+ * 0-based prefix lengths (i, j), type 0 = MATCH, 1 = GAP_1, 2 = GAP_2.  Returns 0, or <0 on the reference's
+ * fatal conditions ("Error Match", "NOT FOUND").  out->type = -1 when the partition is not split. */
+int go_stage4_split_one(const unsigned char* seq0, const unsigned char* seq1, go_xpoint a, go_xpoint b, int max_part, go_xpoint* out);
+/* One reduce_partitions round (:806-852) + merge_partitions (:785-804): returns the new number of crosspoints
+ * written to out (capacity >= 2*n), or <0 on error; *changed tells whether any midpoint was inserted. */
+int go_stage4_round(const unsigned char* seq0, const unsigned char* seq1, const go_xpoint* in, int n, int max_part, go_xpoint* out, int* changed);
+int go_largest_partition(const go_xpoint* pts, int n);
 
 #ifdef __cplusplus
 }

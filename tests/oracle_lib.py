@@ -101,3 +101,40 @@ def read_crosspoints(path):
             t, i, j, s = (int(x) for x in line.split(","))
             pts.append((t, i, j, s))
     return pts
+
+
+XPOINT = np.dtype([("i", "<i4"), ("j", "<i4"), ("type", "<i4"), ("score", "<i4")])     # == crosspoint_t
+
+
+def stage4_round(s0, s1, points, max_part=16):
+    """One reduce_partitions + merge_partitions round of the reference's stage 4 (C restatement). Returns (points, changed)."""
+    L = lib()
+    L.go_stage4_round.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    a = np.ascontiguousarray(s0, dtype=np.uint8); b = np.ascontiguousarray(s1, dtype=np.uint8)
+    pts = np.ascontiguousarray(points, dtype=XPOINT)
+    out = np.zeros(2 * pts.size + 2, XPOINT)
+    ch = C.c_int()
+    n = L.go_stage4_round(a.ctypes.data, b.ctypes.data, pts.ctypes.data, pts.size, max_part, out.ctypes.data, C.byref(ch))
+    assert n > 0, f"stage-4 oracle failed with {n}"
+    return out[:n].copy(), bool(ch.value)
+
+
+def largest_partition(points):
+    L = lib()
+    L.go_largest_partition.argtypes = [C.c_void_p, C.c_int]
+    pts = np.ascontiguousarray(points, dtype=XPOINT)
+    return L.go_largest_partition(pts.ctypes.data, pts.size)
+
+
+def stage4(s0, s1, points, max_part=16):
+    pts = np.ascontiguousarray(points, dtype=XPOINT)
+    while largest_partition(pts) > max_part:
+        pts, changed = stage4_round(s0, s1, pts, max_part)
+        if not changed:
+            break
+    return pts
+
+
+def golden_points(entries):
+    """[(type, i, j, score), ...] as stored in tests/golden -> XPOINT array."""
+    return np.array([(i, j, t, s) for (t, i, j, s) in entries], dtype=XPOINT)

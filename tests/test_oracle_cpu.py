@@ -94,3 +94,13 @@ def test_init_cells():
     assert list(g["h"]) == [0, -5, -7, -9]
     g = O.init_cells(4, O.INIT_GAPS_OPENED)
     assert list(g["h"]) == [0, -2, -4, -6]
+
+
+@pytest.mark.parametrize("name", sorted(GOLD))
+def test_stage4_restatement_matches_reference(name):
+    """ort_split_2 + split_thread + merge_partitions restated in C reproduce the reference's crosspoint_04 file."""
+    g = GOLD[name]
+    a, b = _pair(g["generator"])
+    src = sorted(k for k in g["crosspoints"] if k.startswith("crosspoint_03"))[-1]
+    pts = O.stage4(a, b, O.golden_points(g["crosspoints"][src]), 16)
+    assert np.array_equal(pts, O.golden_points(g["crosspoints"]["crosspoint_04.00"]))
