@@ -12,6 +12,9 @@ static_assert(offsetof(score_t, i) == offsetof(b200_score, i) && offsetof(score_
               offsetof(score_t, score) == offsetof(b200_score, score), "score_t field order");
 static_assert(offsetof(cell_t, h) == offsetof(b200_cell, h) && offsetof(cell_t, f) == offsetof(b200_cell, x), "cell_t field order");
 
+static b200_handle* g_active_handle = NULL;
+b200_handle* B200Aligner::activeHandle() { return g_active_handle; }
+
 B200Aligner::B200Aligner() {
 	params = new B200AlignerParameters();
 	score_params.match = 1;          /* R/src/CUDAligner.hpp:77-98 */
@@ -72,10 +75,12 @@ void B200Aligner::initialize() {
 		fprintf(stderr, "B200Aligner: cannot initialise the GPU: %s\n", b200_last_error(NULL));
 		exit(-1);
 	}
+	g_active_handle = handle;
 }
 
 void B200Aligner::finalize() {
 	if (handle != NULL) {
+		if (g_active_handle == handle) g_active_handle = NULL;
 		b200_destroy(handle);
 		handle = NULL;
 	}

@@ -44,6 +44,9 @@ public:
 	virtual long long getProcessedCells();
 	virtual const char* getProgressString() const;
 
+	/* the handle of the (single) initialised aligner of this process: used by the GPU stage 4 (host/stage4_gpu.cpp) */
+	static b200_handle* activeHandle();
+
 protected:
 	/* AbstractDiagonalAligner virtuals == the ones CUDAligner fills (R/src/CUDAligner.hpp:216-232) */
 	virtual int getGridWidth(int width);
