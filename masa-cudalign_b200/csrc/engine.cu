@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 #include <algorithm>
@@ -60,7 +61,8 @@ struct PinBuf {
 struct b200_handle {
 	b200_config cfg;
 	int sm_count = 0;
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	int* sra_flags = nullptr; size_t sra_flags_cap = 0;     // host-mapped "special row k is complete" flags
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	std::string err;
 
@@ -111,6 +113,7 @@ struct b200_handle {
 		int prune = 0, prune_i1 = 0, prune_j1 = 0;
 		const unsigned char* s0 = nullptr; const unsigned char* s1 = nullptr; Cell* busH = nullptr;
 		int job_off = 0; int* counter = nullptr;
+		int* sra_done = nullptr;
 	} ov;
 	// stage 4
 	struct {
@@ -219,6 +222,7 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.cells_done = reinterpret_cast<unsigned long long*>(h->scalars.p + 4);
 	sp.progress = h->progress.p + h->ov.job_off;
 	sp.results = h->results.p + h->ov.job_off;
+	sp.sra_done = h->ov.sra_done;
 	sp.recurrence = recurrence;
 	sp.track = track;
 	sp.prune = h->ov.prune; sp.prune_i1 = h->ov.prune_i1; sp.prune_j1 = h->ov.prune_j1;
@@ -294,6 +298,7 @@ extern "C" int b200_create(const b200_config* cfg, b200_handle** out) {
 	}
 	h->sm_count = prop.multiProcessorCount;
 	if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+	    (e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess ||
 	    (e = cudaEventCreate(&h->ev0)) != cudaSuccess || (e = cudaEventCreate(&h->ev1)) != cudaSuccess) {
 		g_create_error = cudaGetErrorString(e); delete h; return 3;
 	}
@@ -315,6 +320,8 @@ extern "C" void b200_destroy(b200_handle* h) {
 	b200_mgpu_disconnect(h);
 	cudaEventDestroy(h->ev0); cudaEventDestroy(h->ev1);
 	cudaStreamDestroy(h->stream);
+	cudaStreamDestroy(h->copy_stream);
+	if (h->sra_flags) cudaFreeHost(h->sra_flags);
 	delete h;
 }
 
@@ -418,6 +425,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			j.left_off = r;
 			j.right_off = (p->want_last_column || right_remote) ? r : -1;
 			j.sra_off = sra_off;
+			j.sra_index = sra_off >= 0 ? sra_off / n : -1;
 			h->hjobs.push_back(j);
 			r = end;
 		}
@@ -487,12 +495,48 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	h->ov.prune = (p->prune && sw && track == 2 && kind == B200_KERNEL_S16X2) ? 1 : 0;
 	h->ov.prune_i1 = p->super_i1 > 0 ? p->super_i1 : p->i1;
 	h->ov.prune_j1 = p->super_j1 > 0 ? p->super_j1 : p->j1;
+	// special rows are streamed out while the kernel runs: host-mapped completion flags, one per row
+	const bool stream_rows = have_cb && cb->dispatch_row && !sr_ids.empty();
+	if (stream_rows) {
+		if (h->sra_flags_cap < sr_ids.size()) {
+			if (h->sra_flags) cudaFreeHost(h->sra_flags);
+			h->sra_flags = nullptr; h->sra_flags_cap = 0;
+			CU(h, cudaHostAlloc((void**)&h->sra_flags, (sr_ids.size() + 64) * sizeof(int), cudaHostAllocMapped));
+			h->sra_flags_cap = sr_ids.size() + 64;
+		}
+		memset(h->sra_flags, 0, sr_ids.size() * sizeof(int));
+		h->ov.sra_done = h->sra_flags;
+	}
 	CU(h, cudaEventRecord(h->ev0, h->stream));
 	int lrc = launch_strips(h, njobs, p->recurrence, track, kind, SH, true);
+	h->ov.sra_done = nullptr;
 	h->ov.prune = 0;
 	h->ov.left = nullptr; h->ov.right = nullptr; h->ov.left_ready = nullptr; h->ov.right_ready = nullptr; h->ov.gbest = nullptr; h->ov.npeer = 0;
 	if (lrc) return 1;
 	CU(h, cudaEventRecord(h->ev1, h->stream));
+	size_t rows_streamed = 0;
+	std::vector<int> sr_first_h(sr_ids.size(), 0);
+	if (stream_rows) {
+		// first-column H of every special row (its first dispatched cell), read before the kernel can finish
+		if (p->first_col_init != B200_INIT_ZEROES && !left_remote)
+			for (size_t k = 0; k < sr_ids.size(); k++)
+				CU(h, cudaMemcpyAsync(&sr_first_h[k], &h->left.p[sr_ids[k]].h, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
+		CU(h, cudaStreamSynchronize(h->copy_stream));
+		volatile int* flags = h->sra_flags;
+		while (rows_streamed < sr_ids.size()) {
+			if (!flags[rows_streamed]) {
+				if (cudaStreamQuery(h->stream) != cudaErrorNotReady) { if (!flags[rows_streamed]) break; }   // kernel over (or failed): fall through
+				else { struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr); continue; }
+			}
+			const size_t k = rows_streamed;
+			CU(h, cudaMemcpyAsync(h->hcells.p, h->sra.p + k * (size_t)n, (size_t)n * sizeof(Cell), cudaMemcpyDeviceToHost, h->copy_stream));
+			CU(h, cudaStreamSynchronize(h->copy_stream));
+			b200_cell fc; fc.h = sr_first_h[k]; fc.x = -kInf;
+			cb->dispatch_row(cb->ctx, p->i0 + sr_ids[k], &fc, 1);
+			cb->dispatch_row(cb->ctx, p->i0 + sr_ids[k], reinterpret_cast<b200_cell*>(h->hcells.p), n);
+			rows_streamed++;
+		}
+	}
 	if (track) CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
@@ -542,15 +586,14 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		};
 		(void)first_col_cell;
 		// first-column H values for the first cell of each dispatched row
-		std::vector<int> sr_first_h(sr_ids.size(), 0);
 		int last_first_h = 0;
-		if (p->first_col_init != B200_INIT_ZEROES) {
-			for (size_t k = 0; k < sr_ids.size(); k++)
+		if (p->first_col_init != B200_INIT_ZEROES && !left_remote) {
+			for (size_t k = rows_streamed; k < sr_ids.size(); k++)
 				CU(h, cudaMemcpy(&sr_first_h[k], &h->left.p[sr_ids[k]].h, sizeof(int), cudaMemcpyDeviceToHost));
 			CU(h, cudaMemcpy(&last_first_h, &h->left.p[m].h, sizeof(int), cudaMemcpyDeviceToHost));
 		}
 		if (cb->dispatch_row) {
-			for (size_t k = 0; k < sr_ids.size(); k++) {
+			for (size_t k = rows_streamed; k < sr_ids.size(); k++) {
 				CU(h, cudaMemcpy(h->hcells.p, h->sra.p + k * (size_t)n, (size_t)n * sizeof(Cell), cudaMemcpyDeviceToHost));
 				b200_cell fc; fc.h = sr_first_h[k]; fc.x = -kInf;
 				cb->dispatch_row(cb->ctx, p->i0 + sr_ids[k], &fc, 1);

@@ -41,7 +41,7 @@ struct StripJob {
 	int left_off;           // cell index of slot 0 (corner) of our left border in StripParams::left; slots 1..rows follow
 	int right_off;          // cell index of slot 0 of our right border in StripParams::right, or -1
 	long long sra_off;      // cell index in StripParams::sra where column j0 of our bottom row goes, or -1
-	long long pad;
+	long long sra_index;    // which special row this strip's bottom row is (index into StripParams::sra_done)
 };
 
 struct StripParams {
@@ -63,6 +63,7 @@ struct StripParams {
 	int* right_ready;       // multi-GPU: row counter in the NEXT GPU's exchange block (peer memory), or NULL
 	int* peer_best[8];      // multi-GPU: running-best words of the other GPUs (peer memory)
 	int n_peer_best;
+	int* sra_done;          // host-mapped flags, one per special row: set when the row is complete in the device SRA, or NULL
 	int recurrence;         // B200_SMITH_WATERMAN | B200_NEEDLEMAN_WUNSCH
 	int track;              // 0: no best tracking; 1: exact best cell per job; 2: per job, thresholded by global_best
 	int prune;              // SW block pruning inside the strips (needs track == 2)
@@ -123,6 +124,14 @@ __device__ __forceinline__ void publish_right(const StripParams& p, int upto, in
 	if (p.right_ready == nullptr) return;
 	__syncwarp();
 	if (lane == 0) { __threadfence_system(); st_release_sys(p.right_ready, upto); }
+}
+// tell the host that special row `jb.sra_index` is complete in the device-resident special-rows area, so that it can be
+// copied out and dispatched while the kernel keeps running (replaces the blocking per-block D2H of
+// R/src/CUDAligner.cpp:393-399)
+__device__ __forceinline__ void signal_special_row(const StripParams& p, const StripJob& jb, int lane) {
+	if (p.sra_done == nullptr || jb.sra_off < 0) return;
+	__syncwarp();
+	if (lane == 0) { __threadfence_system(); st_release_sys(p.sra_done + jb.sra_index, 1); }
 }
 __device__ __forceinline__ void push_best(const StripParams& p, int v) {
 	atomicMax(p.global_best, v);

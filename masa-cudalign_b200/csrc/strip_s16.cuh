@@ -453,6 +453,7 @@ struct StripS16 {
 				if (bs != INT_MIN) push_best(p, bs);
 			}
 		}
+		signal_special_row(p, jb, lane);
 		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)computed_cols);
 	}
 };

@@ -185,6 +185,7 @@ struct StripS32 {
 				if (bs != INT_MIN) push_best(p, bs);
 			}
 		}
+		signal_special_row(p, jb, lane);
 		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)cols);
 	}
 };
