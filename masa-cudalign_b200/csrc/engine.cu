@@ -70,6 +70,7 @@ struct b200_handle {
 	DevBuf<unsigned char> s0, s1;
 	int n0 = 0, n1 = 0;
 	bool acgt_only = false;
+	std::vector<unsigned char> bad0;   // per 64 rows of seq0: 1 when the block holds a non-ACGT byte (forces the int32 strip path)
 
 	// strip machinery
 	DevBuf<Cell> busH, left, right, sra;
@@ -114,6 +115,7 @@ struct b200_handle {
 		const unsigned char* s0 = nullptr; const unsigned char* s1 = nullptr; Cell* busH = nullptr;
 		int job_off = 0; int* counter = nullptr;
 		int* sra_done = nullptr;
+		bool mixed = false;
 	} ov;
 	// stage 4
 	struct {
@@ -228,7 +230,10 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.prune = h->ov.prune; sp.prune_i1 = h->ov.prune_i1; sp.prune_j1 = h->ov.prune_j1;
 	const bool sw = recurrence == B200_SMITH_WATERMAN;
 	const void* fn = nullptr;
-	if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F) {
+	if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F && h->ov.mixed) {
+		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16F, true, true, true> : (const void*)strip_kernel_s16<kR16F, true, false, true>;
+		else    fn = track ? (const void*)strip_kernel_s16<kR16F, false, true, true> : (const void*)strip_kernel_s16<kR16F, false, false, true>;
+	} else if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F) {
 		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16F, true, true> : (const void*)strip_kernel_s16<kR16F, true, false>;
 		else    fn = track ? (const void*)strip_kernel_s16<kR16F, false, true> : (const void*)strip_kernel_s16<kR16F, false, false>;
 	} else if (kernel_kind == B200_KERNEL_S16X2) {
@@ -346,6 +351,9 @@ extern "C" int b200_set_sequences(b200_handle* h, const char* seq0, int seq0_len
 		return bad == 0;
 	};
 	h->acgt_only = only_acgt(seq0, seq0_len) && only_acgt(seq1, seq1_len);
+	h->bad0.assign((size_t)seq0_len / 64 + 2, 0);
+	if (!h->acgt_only)
+		for (int k = 0; k < seq0_len; k++) { unsigned char c = (unsigned char)seq0[k]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) h->bad0[k >> 6] = 1; }
 	h->n0 = seq0_len; h->n1 = seq1_len;
 	h->s4.rev_valid = false;
 	CU(h, h->busH.reserve((size_t)seq1_len + 64));
@@ -392,8 +400,8 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	const int m = p->i1 - p->i0, n = p->j1 - p->j0;
 	if (m <= 0 || n <= 0 || p->i0 < 0 || p->j0 < 0 || p->i1 > h->n0 || p->j1 > h->n1) { h->err = "b200_align_partition: partition outside the sequences"; return 1; }
 	CU(h, cudaSetDevice(h->cfg.device));
-	const int kind = pick_kernel(h, 0);
-	const int SH = strip_height(kind, true);
+	int kind = B200_KERNEL_S16X2;                  // decided per strip below; all-int32 partitions use the int32 kernel
+	const int SH = kSH16F;
 	const bool sw = p->recurrence == B200_SMITH_WATERMAN;
 	const int track = p->want_best_score ? 2 : 0;
 	const bool chain = (p->reserved[0] & B200_MGPU_CHAIN) != 0;
@@ -406,14 +414,34 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	std::vector<int> sr_ids;
 	if (p->want_special_rows) special_row_ids(m, bh, p->special_row_interval, sr_ids);
 	h->hjobs.clear();
+	// rows [a, b) of the partition free of non-ACGT bytes?  (64-row granularity, conservative)
+	auto rows_clean = [&](int a, int b) {
+		if (h->acgt_only) return true;
+		for (int k = (p->i0 + a) >> 6; k <= (p->i0 + b - 1) >> 6; k++) if (h->bad0[k]) return false;
+		return true;
+	};
+	bool any_s16 = false, any_s32 = false;
 	{
+		// the packed kernel may be used for a strip iff the caller allows it and the strip's ROWS are pure A/C/G/T
+		// (non-ACGT COLUMN bytes are exact in the packed kernel: they mismatch every A/C/G/T row)
+		const bool allow16 = (h->cfg.kernel == B200_KERNEL_AUTO || h->cfg.kernel == B200_KERNEL_S16X2);
 		size_t next_sr = 0;
 		int r = 0;
 		while (r < m) {
-			int end = std::min(m, r + SH);
+			int lim = m;
+			if (next_sr < sr_ids.size()) lim = std::min(lim, sr_ids[next_sr]);
+			int end;
+			bool s16;
+			if (allow16 && rows_clean(r, std::min(lim, r + kSH32))) {
+				s16 = true;
+				end = std::min(lim, r + kSH32);
+				if (end == r + kSH32 && end < lim && rows_clean(end, std::min(lim, r + kSH16F))) end = std::min(lim, r + kSH16F);
+			} else {
+				s16 = false;
+				end = std::min(lim, r + kSH32);
+			}
 			long long sra_off = -1;
-			if (next_sr < sr_ids.size() && sr_ids[next_sr] <= end) {
-				end = sr_ids[next_sr];
+			if (next_sr < sr_ids.size() && sr_ids[next_sr] == end) {
 				sra_off = (long long)next_sr * n;
 				next_sr++;
 			}
@@ -422,6 +450,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			j.i0 = p->i0 + r; j.rows = end - r; j.j0 = p->j0; j.cols = n;
 			j.dep = (int)h->hjobs.size() - 1;
 			j.flags = (p->first_col_init == B200_INIT_ZEROES && !left_remote) ? JOB_LEFT_ZERO : 0;
+			if (!s16) { j.flags |= JOB_S32; any_s32 = true; } else any_s16 = true;
 			j.left_off = r;
 			j.right_off = (p->want_last_column || right_remote) ? r : -1;
 			j.sra_off = sra_off;
@@ -431,6 +460,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		}
 	}
 	const int njobs = (int)h->hjobs.size();
+	if (!any_s16) kind = B200_KERNEL_S32;
 
 	// ---- buffers
 	CU(h, h->jobs.reserve(njobs));
@@ -507,9 +537,11 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		memset(h->sra_flags, 0, sr_ids.size() * sizeof(int));
 		h->ov.sra_done = h->sra_flags;
 	}
+	h->ov.mixed = any_s16 && any_s32;
 	CU(h, cudaEventRecord(h->ev0, h->stream));
 	int lrc = launch_strips(h, njobs, p->recurrence, track, kind, SH, true);
 	h->ov.sra_done = nullptr;
+	h->ov.mixed = false;
 	h->ov.prune = 0;
 	h->ov.left = nullptr; h->ov.right = nullptr; h->ov.left_ready = nullptr; h->ov.right_ready = nullptr; h->ov.gbest = nullptr; h->ov.npeer = 0;
 	if (lrc) return 1;

@@ -31,6 +31,7 @@ enum JobFlags : int {
 	JOB_LEFT_ZERO = 1,      // left border is the constant (H=0, E=-INF): SW stage 1 first column
 	JOB_PRUNED    = 2,      // do not compute: write -INF to the right border (CUDAligner.cu:950-960 semantics)
 	JOB_TOP_MINF  = 4,      // treat the top border as -INF instead of reading busH (strip above was pruned)
+	JOB_S32       = 8,      // rows of this strip contain a non-ACGT byte: run it with the exact int32 code path
 };
 
 struct StripJob {

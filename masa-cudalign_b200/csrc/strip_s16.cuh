@@ -64,6 +64,13 @@ __device__ __forceinline__ unsigned thr_pack(int thr, int base) {
 	return ((unsigned)v & 0xffffu) | ((unsigned)v << 16);
 }
 __device__ __forceinline__ int code_of(int c) { return (c >> 1) & 3; }     // A->0 C->1 T->2 G->3
+__device__ __forceinline__ bool is_acgt(int c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+// profile word of a column: byte k = score(column, row code k) + 5.  A non-ACGT column byte (N, IUPAC codes, ...)
+// equals no A/C/G/T row byte, so all four entries are the mismatch score -- the reference's raw byte compare
+// (R/src/CUDAligner.cu:282) restricted to strips whose ROWS are pure A/C/G/T (JOB_S32 handles the others).
+__device__ __forceinline__ unsigned profile_word(int c) {
+	return is_acgt(c) ? (0x02020202u ^ (0x04u << (8 * code_of(c)))) : 0x02020202u;
+}
 
 template <int R, bool SW, bool TRACK>
 struct StripS16 {
@@ -377,8 +384,7 @@ struct StripS16 {
 						if (c < cols) {
 							th = tv.h < -kInf / 2 ? kNeg : clamp16(tv.h - s.base);
 							tf = tv.x < -kInf / 2 ? kNeg : clamp16(tv.x - s.base);
-							const int k = code_of(p.s1[j0 + c]);
-							pw = 0x02020202u ^ (0x04u << (8 * k));      // byte k = 6 (match+5), others 2 (mismatch+5)
+							pw = profile_word(p.s1[j0 + c]);              // byte k = 6 (match+5) for the column's base, others 2 (mismatch+5)
 						}
 						sm.topH[warp][lane] = (unsigned)th << 16;
 						sm.topF[warp][lane] = (unsigned)tf << 16;
@@ -458,10 +464,14 @@ struct StripS16 {
 	}
 };
 
-template <int R, bool SW, bool TRACK>
+// MIXED: the launch also contains JOB_S32 strips (rows with N / IUPAC bytes); pure A/C/G/T launches use the lean
+// instantiation (fewer registers, smaller code).
+template <int R, bool SW, bool TRACK, bool MIXED = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 12) strip_kernel_s16(const StripParams p) {
 	using K = StripS16<R, SW, TRACK>;
-	__shared__ typename K::Smem sm;
+	using K32 = StripS32<16, SW, TRACK>;
+	__shared__ union { typename K::Smem s16; typename K32::Smem s32; } smu;
+	typename K::Smem& sm = smu.s16;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	for (;;) {
 		int job = 0;
@@ -481,7 +491,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 12) strip_kernel_s16(cons
 			if (lane == 0) { __threadfence(); st_release(p.progress + job, jb.cols); }
 			continue;
 		}
-		if (rows < K::SH) K::template run_job<true>(p, job, sm, warp, lane);
+		if (MIXED && (flags & JOB_S32)) K32::run_job(p, job, smu.s32, warp, lane);      // rows with N / IUPAC bytes: exact int32 path
+		else if (rows < K::SH) K::template run_job<true>(p, job, sm, warp, lane);
 		else K::template run_job<false>(p, job, sm, warp, lane);
 	}
 }

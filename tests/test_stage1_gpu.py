@@ -109,3 +109,25 @@ def test_pruning_keeps_best_exact(b200, m, n, hom):
         o = O.full_matrix(a, b, O.SW, want_last_col=False)
         assert r["best"] == o["best"]
     al.close()
+
+
+def test_mixed_alphabet_matches_byte_compare(b200):
+    """Real FASTA files carry N runs and IUPAC codes; the reference compares raw bytes (N == N matches).  Strips whose
+    rows hold such bytes take the int32 code path inside the same launch, the others stay on the packed kernel."""
+    m, n = 9000, 7000
+    a, b = synth.make_pair(m, n, [(1000, 8000)], 0.05, 0.01, 0.01, 0, 17)
+    a = a.copy(); b = b.copy()
+    a[2000:2300] = ord("N"); b[1700:2100] = ord("N")          # overlapping N runs: N-N cells score +1
+    a[5000] = ord("R"); a[5001] = ord("n"); b[4000:4005] = np.frombuffer(b"RYKMN", dtype=np.uint8)
+    al = b200.Aligner()                                        # KERNEL_AUTO
+    al.set_sequences(a, b)
+    r = al.align_partition(want_last_row=True, want_last_column=True, want_special_rows=True, special_row_interval=1000)
+    assert r["kernel_used"] == b200.KERNEL_S16X2               # mixed launch: most strips are still packed
+    o = O.full_matrix(a, b, O.SW, row_ids=[8191, m - 1])
+    assert r["best"] == o["best"]
+    assert np.array_equal(r["rows"][8192], o["rows"][8191])
+    assert np.array_equal(r["rows"][m], o["rows"][m - 1])
+    assert np.array_equal(r["last_column"], o["last_col"])
+    rp = al.align_partition(prune=True)
+    assert rp["best"] == o["best"]
+    al.close()
