@@ -35,14 +35,14 @@ extern "C" {
 
 #define B200_INF 999999999            /* C/libmasa/libmasaTypes.hpp:46 */
 
-#define B200_SMITH_WATERMAN 1         /* C/libmasa/IManager.hpp SMITH_WATERMAN   */
-#define B200_NEEDLEMAN_WUNSCH 2       /* C/libmasa/IManager.hpp NEEDLEMAN_WUNSCH */
+#define B200_NEEDLEMAN_WUNSCH 0       /* == NEEDLEMAN_WUNSCH, C/libmasa/IManager.hpp:31 */
+#define B200_SMITH_WATERMAN 1         /* == SMITH_WATERMAN,   C/libmasa/IManager.hpp:33 */
 
-/* first row / first column sources (C/common/io/InitialCellsReader.cpp:84-108, CellsReader types) */
+/* first row / first column sources: values of C/libmasa/IManager.hpp:38-47, cells of C/common/io/InitialCellsReader.cpp:84-108 */
 #define B200_INIT_ZEROES 0            /* h = 0,                   e/f = -INF */
 #define B200_INIT_GAPS 1              /* h = -ext*pos - open,     e/f = -INF; pos 0 -> h = 0 */
-#define B200_INIT_GAPS_OPENED 2       /* h = -ext*pos,            e/f = -INF */
-#define B200_INIT_CUSTOM 3            /* cells supplied by the caller */
+#define B200_INIT_CUSTOM 2            /* == INIT_WITH_CUSTOM_DATA (:47): cells supplied by the caller */
+#define B200_INIT_GAPS_OPENED 3       /* == INIT_WITH_GAPS_OPENED (:44): h = -ext*pos, e/f = -INF */
 
 /* kernel selection */
 #define B200_KERNEL_AUTO 0
@@ -74,8 +74,17 @@ typedef struct {
 	int want_best_score;         /* IManager::mustDispatchScores: exact best cell of the partition */
 	int prune;                   /* IManager::mustPruneBlocks */
 	int super_i1, super_j1;      /* IManager::getSuperPartition: bounds used by the pruning test */
-	int reserved[4];
+	int reserved[4];             /* [0] flags: B200_MGPU_CHAIN | B200_CONT_CHUNK; [1] column offset of a chained slice;
+	                                [2] rows of the partition already aligned by earlier chunk calls; [3] total rows of
+	                                the partition (0 = i1-i0): the special-row policy is applied to the WHOLE partition */
 } b200_partition;
+
+/* B200_CONT_CHUNK: this call continues the previous b200_align_partition call of the same handle one chunk of rows
+ * further down (same columns): the top border is taken from the device (it is the previous chunk's last row), the
+ * corner cells are not read again, receive_first_column continues where it stopped, and the first cell of the last
+ * column is not dispatched again.  Used by the adapter to run stage-2/3 partitions (goal matching on the last column,
+ * early stop) as a few persistent launches instead of one launch per external diagonal. */
+#define B200_CONT_CHUNK 2
 
 /* Callbacks == the IManager methods the reference aligner calls (C/libmasa/IManager.hpp:150-313).
  * Buffers passed to dispatch_* are borrowed for the duration of the call. May be NULL when not needed. */

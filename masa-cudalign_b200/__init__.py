@@ -14,8 +14,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb200align.so")
 
 INF = 999999999
-SMITH_WATERMAN, NEEDLEMAN_WUNSCH = 1, 2
-INIT_ZEROES, INIT_GAPS, INIT_GAPS_OPENED, INIT_CUSTOM = 0, 1, 2, 3
+NEEDLEMAN_WUNSCH, SMITH_WATERMAN = 0, 1                          # C/libmasa/IManager.hpp:31-33
+INIT_ZEROES, INIT_GAPS, INIT_CUSTOM, INIT_GAPS_OPENED = 0, 1, 2, 3    # C/libmasa/IManager.hpp:38-47
 KERNEL_AUTO, KERNEL_S32, KERNEL_S16X2 = 0, 1, 2
 
 CELL = np.dtype([("h", "<i4"), ("x", "<i4")])

@@ -95,6 +95,7 @@ struct b200_handle {
 		bool col0_valid[2] = {false, false};
 		int last_diag = -1;
 		std::vector<b200_score> scores;
+		PinBuf<Cell> hlastcol; int hlastcol_diag = -2;
 	} dg;
 
 	// multi-GPU chain: exchange block = [64 control ints][max_rows+1 cells]; ctrl[0] = rows of our left border
@@ -125,6 +126,7 @@ struct b200_handle {
 		DevBuf<S4Half> halves; DevBuf<S4Part> parts; DevBuf<XPoint> out;
 	} s4;
 
+	Cell cont_corner;              // first-column cell of the last row of the previous chunk (B200_CONT_CHUNK)
 	long long stat_cells = 0;
 	long long stat_launches = 0;
 };
@@ -293,6 +295,7 @@ extern "C" int b200_create(const b200_config* cfg, b200_handle** out) {
 	b200_handle* h = new b200_handle();
 	memset(&h->cfg, 0, sizeof(h->cfg));
 	if (cfg) h->cfg = *cfg;
+	h->cont_corner.h = 0; h->cont_corner.x = -kInf;
 	if (h->cfg.device < 0 || h->cfg.device >= ndev) h->cfg.device = h->cfg.device < 0 ? 0 : h->cfg.device % ndev;   // wrap like R/src/CUDAligner.cpp:142-148
 	if ((e = cudaSetDevice(h->cfg.device)) != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return 3; }
 	cudaDeviceProp prop;
@@ -319,7 +322,7 @@ extern "C" void b200_destroy(b200_handle* h) {
 	h->s0.release(); h->s1.release(); h->busH.release(); h->left.release(); h->right.release(); h->sra.release();
 	h->jobs.release(); h->progress.release(); h->results.release(); h->scalars.release();
 	h->hcells.release(); h->hresults.release(); h->hscalars.release();
-	h->dg.vbuf.release(); h->dg.col0.release();
+	h->dg.vbuf.release(); h->dg.col0.release(); h->dg.hlastcol.release();
 	h->s4.s0r.release(); h->s4.s1r.release(); h->s4.left.release(); h->s4.halves.release(); h->s4.parts.release(); h->s4.out.release();
 	for (int k = 0; k < 4; k++) h->s4.bus[k].release();
 	b200_mgpu_disconnect(h);
@@ -405,6 +408,9 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	const bool sw = p->recurrence == B200_SMITH_WATERMAN;
 	const int track = p->want_best_score ? 2 : 0;
 	const bool chain = (p->reserved[0] & B200_MGPU_CHAIN) != 0;
+	const bool cont = (p->reserved[0] & B200_CONT_CHUNK) != 0;
+	const int row_offset = p->reserved[2];
+	const int total_rows = p->reserved[3] > 0 ? p->reserved[3] : m;
 	if (chain && (!h->mg.connected || (size_t)m > h->mg.max_rows)) { h->err = "b200_align_partition: multi-GPU chain requested but b200_mgpu_connect was not called (or max_rows too small)"; return 1; }
 	const bool left_remote = chain && h->mg.rank > 0;
 	const bool right_remote = chain && h->mg.rank + 1 < h->mg.world;
@@ -412,7 +418,11 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	// ---- special rows and strips
 	int bh = p->block_height > 0 ? p->block_height : 4 * std::min(128, n);
 	std::vector<int> sr_ids;
-	if (p->want_special_rows) special_row_ids(m, bh, p->special_row_interval, sr_ids);
+	if (p->want_special_rows) {
+		std::vector<int> all_ids;
+		special_row_ids(total_rows, bh, p->special_row_interval, all_ids);
+		for (int g : all_ids) if (g > row_offset && g <= row_offset + m) sr_ids.push_back(g - row_offset);
+	}
 	h->hjobs.clear();
 	// rows [a, b) of the partition free of non-ACGT bytes?  (64-row granularity, conservative)
 	auto rows_clean = [&](int a, int b) {
@@ -479,10 +489,13 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	Cell corner_col; corner_col.h = 0; corner_col.x = -kInf;
 	Cell corner_row = corner_col;
 	const bool have_cb = cb != nullptr;
-	if (have_cb && cb->receive_first_column) cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(&corner_col), 1);
-	if (have_cb && cb->receive_first_row) cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(&corner_row), 1);
+	if (cont) corner_col = h->cont_corner;
+	if (!cont && have_cb && cb->receive_first_column) cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(&corner_col), 1);
+	if (!cont && have_cb && cb->receive_first_row) cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(&corner_row), 1);
 	Cell first_row_tail = corner_row;
-	if (p->first_row_init == B200_INIT_ZEROES || !(have_cb && cb->receive_first_row)) {
+	if (cont) {
+		// top border = last row of the previous chunk, already in busH
+	} else if (p->first_row_init == B200_INIT_ZEROES || !(have_cb && cb->receive_first_row)) {
 		int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
 		fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1 + p->reserved[1], 0);   // reserved[1]: column offset of a chained slice
 		h->stat_launches++;
@@ -498,11 +511,12 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		if (have_cb && cb->receive_first_column) {
 			h->hcells.p[0] = corner_col;
 			cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p + 1), m);
+			h->cont_corner = h->hcells.p[m];
 			CU(h, cudaMemcpyAsync(h->left.p, h->hcells.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 			CU(h, cudaStreamSynchronize(h->stream));
 		} else {
 			int type = p->first_col_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_col_init;
-			fill_cells_kernel<<<(m + 1 + 255) / 256, 256, 0, h->stream>>>(h->left.p, (long long)m + 1, type, 0, 0);
+			fill_cells_kernel<<<(m + 1 + 255) / 256, 256, 0, h->stream>>>(h->left.p, (long long)m + 1, type, row_offset, 0);
 			h->stat_launches++;
 		}
 	}
@@ -641,7 +655,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		if (cb->dispatch_column && p->want_last_column && !right_remote) {
 			CU(h, cudaMemcpy(h->hcells.p, h->right.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyDeviceToHost));
 			b200_cell fc; fc.h = first_row_tail.h; fc.x = -kInf;
-			cb->dispatch_column(cb->ctx, p->j1, &fc, 1);
+			if (!cont) cb->dispatch_column(cb->ctx, p->j1, &fc, 1);
 			for (int r = 0; r < m; r += bh) {
 				int len = std::min(bh, m - r);
 				cb->dispatch_column(cb->ctx, p->j1, reinterpret_cast<b200_cell*>(h->hcells.p + 1 + r), len);
@@ -677,7 +691,7 @@ extern "C" int b200_diag_begin(b200_handle* h, const b200_partition* p, int grid
 	CU(h, h->scalars.reserve(8));
 	CU(h, h->hscalars.reserve(8));
 	d.col0_cur = 0; d.col0_valid[0] = d.col0_valid[1] = false;
-	d.last_diag = -1;
+	d.last_diag = -1; d.hlastcol_diag = -2;
 	b200_score z; z.score = -kInf; z.i = -1; z.j = -1;
 	d.scores.assign(grid_width, z);
 	d.active = true;
@@ -760,9 +774,17 @@ extern "C" int b200_diag_process(b200_handle* h, int diagonal, int window_left, 
 	if (rc) return 1;
 	CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, njobs * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	{
+		// the last block column's right border of this diagonal travels with the results (one sync per diagonal);
+		// b200_diag_get_last_column then serves it from pinned host memory
+		const int parn = (diagonal + 1) & 1;
+		CU(h, d.hlastcol.reserve(slot));
+		CU(h, cudaMemcpyAsync(d.hlastcol.p, d.vbuf.p + ((size_t)parn * (d.B + 1) + d.B) * slot, slot * sizeof(Cell), cudaMemcpyDeviceToHost, h->stream));
+	}
 	CU(h, cudaStreamSynchronize(h->stream));
 	CU(h, cudaGetLastError());
 	if (h->hscalars.p[2] != 0) { h->err = "strip kernel watchdog: a border dependency did not advance"; return 5; }
+	d.hlastcol_diag = diagonal;
 	for (int k = 0; k < njobs; k++) {
 		const Score3& s = h->hresults.p[k];
 		b200_score& o = d.scores[job_bx[k]];
@@ -789,6 +811,7 @@ extern "C" int b200_diag_get_last_column(b200_handle* h, int i, int len, b200_ce
 	if (!out || len < 0 || len > d.bh) { h->err = "b200_diag_get_last_column: bad range"; return 1; }
 	// the last block column wrote its right border for the diagonal just processed into parity (last_diag+1)&1, slot B
 	const size_t slot = (size_t)d.bh + 1;
+	if (d.hlastcol_diag == d.last_diag && d.hlastcol.p) { memcpy(out, d.hlastcol.p + 1, (size_t)len * sizeof(Cell)); return 0; }
 	const int par = (d.last_diag + 1) & 1;
 	CU(h, cudaMemcpyAsync(out, d.vbuf.p + ((size_t)par * (d.B + 1) + d.B) * slot + 1, (size_t)len * sizeof(Cell), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));

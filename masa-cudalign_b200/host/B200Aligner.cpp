@@ -27,7 +27,8 @@ B200Aligner::B200Aligner() {
 	fastActive = false;
 	fastCells = 0;
 	fastDeviceMs = 0;
-	fastPartitions = diagPartitions = 0;
+	fastPartitions = diagPartitions = chunkPartitions = chunkLaunches = 0;
+	bufferingTail = false; tailFirstCellSeen = false;
 }
 
 B200Aligner::~B200Aligner() {}
@@ -114,20 +115,35 @@ bool B200Aligner::canUseFastPath() {
 	return true;
 }
 
+/* Stage 2/3 partitions of the common kind: the goal is matched on the LAST COLUMN (AT_SEQUENCE_1_OR_2,
+ * C/stage2/sw_stage2.cpp:80-88), nothing depends on per-block scores.  The last column is a sequential stream
+ * (first hit wins, C/common/AlignerManager.cpp:334-369), so the partition can be aligned in chunks of rows, each one
+ * persistent launch, dispatching the column chunks in order and stopping after the chunk in which the manager found
+ * its crosspoint: identical crosspoints, ~100x fewer launches than one per external diagonal. */
+bool B200Aligner::canUseChunkPath() {
+	if (!params->useFastPath()) return false;
+	if (!mustDispatchLastColumn()) return false;
+	if (mustDispatchScores() || mustDispatchLastCell() || mustPruneBlocks()) return false;
+	if (mustDispatchSpecialColumns()) return false;
+	return true;
+}
+
 void B200Aligner::alignPartition(Partition partition) {
+	static const bool dbg = getenv("B200_DEBUG") != NULL;
+	if (dbg) fprintf(stderr, "[B200Aligner] partition %dx%d lastcol=%d scores=%d lastrow=%d lastcell=%d prune=%d srows=%d rec=%d\n",
+			partition.getHeight(), partition.getWidth(), (int)mustDispatchLastColumn(), (int)mustDispatchScores(), (int)mustDispatchLastRow(),
+			(int)mustDispatchLastCell(), (int)mustPruneBlocks(), (int)mustDispatchSpecialRows(), getRecurrenceType());
 	if (canUseFastPath()) {
 		alignPartitionFast(partition);
+	} else if (canUseChunkPath()) {
+		alignPartitionChunked(partition);
 	} else {
 		diagPartitions++;
 		AbstractDiagonalAligner::alignPartition(partition);
 	}
 }
 
-void B200Aligner::alignPartitionFast(Partition partition) {
-	fastPartitions++;
-	fastPartition = partition;
-	fastActive = true;
-	b200_partition p;
+void B200Aligner::fillPartition(b200_partition& p, Partition partition) {
 	memset(&p, 0, sizeof(p));
 	p.i0 = partition.getI0(); p.j0 = partition.getJ0(); p.i1 = partition.getI1(); p.j1 = partition.getJ1();
 	p.recurrence = getRecurrenceType();
@@ -138,11 +154,99 @@ void B200Aligner::alignPartitionFast(Partition partition) {
 	p.block_height = (width <= B200_THREADS_COUNT ? width : B200_THREADS_COUNT) * B200_ALPHA;
 	p.want_special_rows = mustDispatchSpecialRows() && getSpecialRowInterval() > 0;
 	p.want_last_row = mustDispatchLastRow() || mustDispatchLastCell();
-	p.want_last_column = 0;
+	p.want_last_column = mustDispatchLastColumn();
 	p.want_best_score = mustDispatchScores();
 	p.prune = mustPruneBlocks();
 	Partition sp = getSuperPartition();
 	p.super_i1 = sp.getI1(); p.super_j1 = sp.getJ1();
+}
+
+void B200Aligner::alignPartitionChunked(Partition partition) {
+	chunkPartitions++;
+	fastPartition = partition;
+	fastActive = true;
+	b200_callbacks cb;
+	memset(&cb, 0, sizeof(cb));
+	cb.ctx = this;
+	cb.receive_first_row = cbReceiveFirstRow;
+	cb.receive_first_column = cbReceiveFirstColumn;
+	cb.dispatch_row = cbDispatchRow;
+	cb.dispatch_column = cbDispatchColumn;
+	cb.dispatch_score = cbDispatchScore;
+	cb.must_continue = cbMustContinue;
+	const int height = partition.getHeight(), width = partition.getWidth();
+	const int bh = (width <= B200_THREADS_COUNT ? width : B200_THREADS_COUNT) * B200_ALPHA;
+	const int B = getGridWidth(width);
+	const bool wantLastRow = mustDispatchLastRow();
+	/* The path the manager is looking for is roughly diagonal: it leaves a partition of this width after about
+	 * `width` rows.  Chunks are whole blocks, at least B block-rows (2*width rows) so that, in the reference's
+	 * external-diagonal order, every last-column chunk of an earlier launch precedes the first last-row piece
+	 * (column chunk `by` leaves at diagonal by+B, row piece p at diagonal gridHeight+p). */
+	long long target = 2LL * width;
+	if (target < 8192) target = 8192;
+	if (target > 131072) target = 131072;
+	int chunk = (int)(((target + bh - 1) / bh) * bh);
+	if (chunk < B * bh) chunk = B * bh;
+	for (int off = 0; off < height && mustContinue();) {
+		int rows = chunk;
+		if (height - (off + rows) < B * bh) rows = height - off;      /* never leave a short tail chunk */
+		if (off + rows > height) rows = height - off;
+		const bool finalChunk = off + rows >= height;
+		b200_partition p;
+		fillPartition(p, partition);
+		p.i0 = partition.getI0() + off;
+		p.i1 = p.i0 + rows;
+		p.want_last_row = (finalChunk && wantLastRow) ? 1 : 0;
+		p.want_best_score = 0;
+		p.prune = 0;
+		p.reserved[0] = off > 0 ? B200_CONT_CHUNK : 0;
+		p.reserved[2] = off;
+		p.reserved[3] = height;
+		bufferingTail = finalChunk && wantLastRow;
+		tailFirstCellSeen = off > 0;                /* the corner cell of the last column is dispatched by the first chunk only */
+		tailCol.clear(); tailRow.clear();
+		b200_result res;
+		check(b200_align_partition(handle, &p, &cb, &res), "b200_align_partition (chunk)");
+		fastCells += res.cells;
+		fastDeviceMs += res.device_ms;
+		chunkLaunches++;
+		if (bufferingTail) {
+			bufferingTail = false;
+			/* replay in the order of AbstractDiagonalAligner::processNextIteration (flushLastRow before
+			 * flushLastColumn inside one external diagonal, AbstractDiagonalAligner.cpp:120-130,325-369) */
+			Grid* grid = createGrid(partition);
+			grid->setBlockHeight(bh);
+			grid->splitGridHorizontally(B);
+			const int gh = height / bh + 1;
+			const int by0 = off / bh;
+			for (int d = 0; d <= gh + B && mustContinue(); d++) {
+				const int piece = d - gh;
+				if (piece >= 0 && piece < B && !tailRow.empty()) {
+					int x0, x1;
+					grid->getBlockPosition(piece, 0, NULL, &x0, NULL, &x1);
+					if (piece == 0) dispatchRow(partition.getI1(), &tailRowFirst, 1);
+					if (mustContinue()) dispatchRow(partition.getI1(), &tailRow[x0 - partition.getJ0()], x1 - x0);
+				}
+				const int by = d - B;
+				if (mustContinue() && by >= by0 && (long long)by * bh < height) {
+					const int r0 = by * bh - off;
+					const int len = (by * bh + bh <= height) ? bh : height - by * bh;
+					if (r0 >= 0 && r0 + len <= (int)tailCol.size()) dispatchColumn(partition.getJ1(), &tailCol[r0], len);
+				}
+			}
+		}
+		off += rows;
+	}
+	fastActive = false;
+}
+
+void B200Aligner::alignPartitionFast(Partition partition) {
+	fastPartitions++;
+	fastPartition = partition;
+	fastActive = true;
+	b200_partition p;
+	fillPartition(p, partition);
+	p.want_last_column = 0;
 
 	b200_callbacks cb;
 	memset(&cb, 0, sizeof(cb));
@@ -169,6 +273,11 @@ void B200Aligner::cbReceiveFirstColumn(void* ctx, b200_cell* buffer, int len) {
 void B200Aligner::cbDispatchRow(void* ctx, int i, const b200_cell* buffer, int len) {
 	B200Aligner* a = (B200Aligner*)ctx;
 	const bool last = (i == a->fastPartition.getI1());
+	if (last && a->bufferingTail) {
+		if (len == 1 && a->tailRow.empty()) { a->tailRowFirst = *(const cell_t*)buffer; return; }
+		a->tailRow.insert(a->tailRow.end(), (const cell_t*)buffer, (const cell_t*)buffer + len);
+		return;
+	}
 	if (last && !a->mustDispatchLastRow()) {
 		/* only the last CELL was asked for (bestScoreLocation == AT_SEQUENCE_1_AND_2): AbstractDiagonalAligner::flushLastCell */
 		if (len > 1 && a->mustDispatchLastCell()) {
@@ -190,15 +299,23 @@ void B200Aligner::cbDispatchRow(void* ctx, int i, const b200_cell* buffer, int l
 	}
 }
 void B200Aligner::cbDispatchColumn(void* ctx, int j, const b200_cell* buffer, int len) {
-	((B200Aligner*)ctx)->dispatchColumn(j, (const cell_t*)buffer, len);
+	B200Aligner* a = (B200Aligner*)ctx;
+	if (a->bufferingTail) {
+		if (!a->tailFirstCellSeen) { a->tailFirstCellSeen = true; a->dispatchColumn(j, (const cell_t*)buffer, len); return; }   /* corner cell */
+		a->tailCol.insert(a->tailCol.end(), (const cell_t*)buffer, (const cell_t*)buffer + len);
+		return;
+	}
+	a->dispatchColumn(j, (const cell_t*)buffer, len);
 }
+
 void B200Aligner::cbDispatchScore(void* ctx, b200_score score) {
 	score_t s;
 	s.i = score.i; s.j = score.j; s.score = score.score;
 	((B200Aligner*)ctx)->dispatchScore(s);
 }
 int B200Aligner::cbMustContinue(void* ctx) {
-	return ((B200Aligner*)ctx)->mustContinue() ? 1 : 0;
+	B200Aligner* a = (B200Aligner*)ctx;
+	return (a->bufferingTail || a->mustContinue()) ? 1 : 0;      /* while buffering, nothing has reached the manager yet */
 }
 
 /* ------------------------------------------------------------------------------------------------------------
@@ -316,8 +433,8 @@ void B200Aligner::printStageStatistics(FILE* file) {
 }
 
 void B200Aligner::printFinalStatistics(FILE* file) {
-	fprintf(file, "B200 partitions: %lld whole-partition (persistent kernel), %lld per-diagonal; kernel launches: %lld\n",
-			fastPartitions, diagPartitions, handle ? b200_kernel_launches(handle) : 0LL);
+	fprintf(file, "B200 partitions: %lld whole-partition (persistent kernel), %lld chunked (%lld launches), %lld per-diagonal; kernel launches: %lld\n",
+			fastPartitions, chunkPartitions, chunkLaunches, diagPartitions, handle ? b200_kernel_launches(handle) : 0LL);
 }
 
 void B200Aligner::printStatistics(FILE* file) {

@@ -71,14 +71,23 @@ private:
 	bool fastActive;
 	long long fastCells;
 	double fastDeviceMs;
-	long long fastPartitions, diagPartitions;
+	long long fastPartitions, diagPartitions, chunkPartitions, chunkLaunches;
 	Partition fastPartition;
+	/* final chunk of a chunked partition: last row and last-column chunks are buffered and replayed in the
+	 * reference's external-diagonal order (see alignPartitionChunked) */
+	bool bufferingTail;
+	bool tailFirstCellSeen;
+	std::vector<cell_t> tailCol, tailRow;
+	cell_t tailRowFirst;
 	std::vector<cell_t> rowBuffer, colBuffer;
 	std::vector<score_t> scoreBuffer;
 
 	void check(int rc, const char* what);
 	bool canUseFastPath();
+	bool canUseChunkPath();
 	void alignPartitionFast(Partition partition);
+	void alignPartitionChunked(Partition partition);
+	void fillPartition(b200_partition& p, Partition partition);
 
 	/* C callbacks of b200_align_partition -> IManager delegates */
 	static void cbReceiveFirstRow(void* ctx, b200_cell* buffer, int len);

@@ -11,14 +11,14 @@ typedef struct { int found, k, score, type; } go_match;   /* libmasaTypes.hpp:51
 typedef struct { int i, j, type, score; } go_xpoint;      /* == crosspoint_t, common/Crosspoint.hpp:30-40 */
 
 #define GO_INF 999999999
-#define GO_SW 1   /* SMITH_WATERMAN  (libmasa/IManager.hpp) */
-#define GO_NW 2   /* NEEDLEMAN_WUNSCH */
+#define GO_NW 0   /* NEEDLEMAN_WUNSCH (libmasa/IManager.hpp:31) */
+#define GO_SW 1   /* SMITH_WATERMAN   (libmasa/IManager.hpp:33) */
 
 /* init types (common/io/InitialCellsReader.cpp:84-108) */
 #define GO_INIT_ZEROES 0
 #define GO_INIT_GAPS 1          /* h = -ext*pos - open  */
-#define GO_INIT_GAPS_OPENED 2   /* h = -ext*pos         */
-#define GO_INIT_CUSTOM 3
+#define GO_INIT_CUSTOM 2        /* INIT_WITH_CUSTOM_DATA (libmasa/IManager.hpp:47) */
+#define GO_INIT_GAPS_OPENED 3   /* h = -ext*pos         (libmasa/IManager.hpp:44) */
 
 int go_full_matrix(const unsigned char* s0, int m, const unsigned char* s1, int n, int recurrence,
                    const go_cell* first_row /*n+1 or NULL*/, int first_row_type,

@@ -10,8 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 CELL = np.dtype([("h", "<i4"), ("x", "<i4")])
 INF = 999999999
-SW, NW = 1, 2
-INIT_ZEROES, INIT_GAPS, INIT_GAPS_OPENED, INIT_CUSTOM = 0, 1, 2, 3
+NW, SW = 0, 1
+INIT_ZEROES, INIT_GAPS, INIT_CUSTOM, INIT_GAPS_OPENED = 0, 1, 2, 3
 
 
 class GoScore(C.Structure):

@@ -65,7 +65,7 @@ def run_diag(b200, al, a, b, i0, j0, i1, j1, rec, fr, fc, frt, fct, B, bh, windo
 
 
 @pytest.mark.parametrize("kernel", ["s32", "s16x2"])
-@pytest.mark.parametrize("rec,frt,fct", [("sw", 0, 0), ("nw", 1, 1), ("nw", 2, 1), ("nw", 1, 2)])
+@pytest.mark.parametrize("rec,frt,fct", [("sw", 0, 0), ("nw", 1, 1), ("nw", 3, 1), ("nw", 1, 3)])
 @pytest.mark.parametrize("m,n,B,bh", [(3000, 2700, 5, 512), (5000, 1300, 2, 512), (700, 100, 1, 400), (1537, 4096, 8, 512)])
 def test_diag_matches_oracle(b200, kernel, rec, frt, fct, m, n, B, bh):
     a, b = synth.make_pair(m + 100, n + 50, [(300, m - 200)], 0.05, 0.02, 0.02, 0, 5)
