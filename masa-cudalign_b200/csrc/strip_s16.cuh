@@ -396,7 +396,7 @@ struct StripS16 {
 				// ---- 32 steps; the check-free body runs whenever every virtual lane is inside [c0, c1)
 				const bool steady = (tb >= c0 + V) && (tb + 32 < c1);
 				if (steady) {
-#pragma unroll 1
+#pragma unroll 2
 					for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
 				} else {
 #pragma unroll 1
