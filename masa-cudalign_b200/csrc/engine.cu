@@ -551,7 +551,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		memset(h->sra_flags, 0, sr_ids.size() * sizeof(int));
 		h->ov.sra_done = h->sra_flags;
 	}
-	h->ov.mixed = any_s16 && any_s32;
+	h->ov.mixed = !h->acgt_only;      // N / IUPAC bytes anywhere: PRMT variant (+ int32 strips); pure A/C/G/T: LUT variant
 	CU(h, cudaEventRecord(h->ev0, h->stream));
 	int lrc = launch_strips(h, njobs, p->recurrence, track, kind, SH, true);
 	h->ov.sra_done = nullptr;

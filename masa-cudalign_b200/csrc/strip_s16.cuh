@@ -72,17 +72,23 @@ __device__ __forceinline__ unsigned profile_word(int c) {
 	return is_acgt(c) ? (0x02020202u ^ (0x04u << (8 * code_of(c)))) : 0x02020202u;
 }
 
-template <int R, bool SW, bool TRACK>
+// LUT: fetch the packed substitution scores of a row pair with one conflict-free LDS from a table replicated per
+// lane (lut[dq*16+cq][lane], dq = column codes of the two halves, cq = row codes) instead of the PRMT byte-select:
+// PRMT issues at half the VIADDMNMX rate (profiles/r01_pipe_rates.txt) and the kernel is bound by that pipe, the LSU
+// is idle.  Needs both sequences to be pure A/C/G/T (the PRMT variant serves launches with N / IUPAC columns).
+constexpr int kLutBytes = 256 * 32 * 4;
+
+template <int R, bool SW, bool TRACK, bool LUT = false>
 struct StripS16 {
 	static constexpr int V = 64;
 	static constexpr int SH = V * R;
 
 	struct Smem {
-		unsigned topH[kWarpsPerBlock][32];   // H<<16 of the top border in the local frame (lane 0 injects it into its low half)
-		unsigned topF[kWarpsPerBlock][32];   // F<<16
-		unsigned prof[kWarpsPerBlock][32];   // column profile words: byte k = s(k, column base) + 5
-		uint2 bot[kWarpsPerBlock][64];       // packed (H,F) registers of the lane that owns the bottom row, ring over columns
-		unsigned cand[kWarpsPerBlock][kCand][R + 2];   // deferred best-cell candidates: T[0..R) of a lane + {step, lane|halves<<8}
+		unsigned topH[32];   // H<<16 of the top border in the local frame (lane 0 injects it into its low half)
+		unsigned topF[32];   // F<<16
+		unsigned prof[32];   // column profile words: byte k = s(k, column base) + 5
+		uint2 bot[64];       // packed (H,F) registers of the lane that owns the bottom row, ring over columns
+		unsigned cand[kCand][R + 2];   // deferred best-cell candidates: T[0..R) of a lane + {step, lane|halves<<8}
 	};
 
 	// all per-warp state of one job
@@ -90,6 +96,7 @@ struct StripS16 {
 		unsigned T[R], E[R], sel[R];
 		unsigned tprev, botH, botF, pa, pb;
 		unsigned Zp, thrp, blk;
+		unsigned lut;                        // shared-memory address of lut[0][lane] (LUT variant)
 		int base;
 		int bs, bi, bj, thr, pub, ncand;
 	};
@@ -101,7 +108,7 @@ struct StripS16 {
 		unsigned shH = __shfl_up_sync(0xffffffffu, s.botH, 1);
 		unsigned shF = __shfl_up_sync(0xffffffffu, s.botF, 1);
 		unsigned shP = __shfl_up_sync(0xffffffffu, s.pb, 1);
-		if (lane == 0) { shH = sm.topH[warp][u]; shF = sm.topF[warp][u]; shP = sm.prof[warp][u]; }   // predicated LDS, no SEL
+		if (lane == 0) { shH = sm.topH[u]; shF = sm.topF[u]; shP = sm.prof[u]; }   // predicated LDS, no SEL
 		const unsigned upH = prmt(shH, s.botH, 0x5432);      // lo <- neighbour's hi, hi <- own lo
 		const unsigned upF = prmt(shF, s.botF, 0x5432);
 		s.pb = s.pa; s.pa = shP;
@@ -120,9 +127,13 @@ struct StripS16 {
 				if (col_hi < c0) keep |= 0xffff0000u;
 			}
 			s.tprev = CHECK ? ((tup & ~keep) | (s.tprev & keep)) : tup;
+			unsigned lrow = 0;
+			if (LUT) lrow = s.lut + ((s.pa | (s.pb << 2)) << 11);      // table rows of this step's two column codes
 #pragma unroll
 			for (int r = 0; r < R; r++) {
-				const unsigned sc = prmt(s.pa, s.pb, s.sel[r]);
+				unsigned sc;
+				if (LUT) asm("ld.shared.u32 %0, [%1];" : "=r"(sc) : "r"(lrow + s.sel[r]));
+				else sc = prmt(s.pa, s.pb, s.sel[r]);
 				const unsigned e = __viaddmax_s16x2(s.E[r], M2, s.T[r]);
 				const unsigned x = SW ? __viaddmax_s16x2(dT, sc, s.Zp) : __vadd2(dT, sc);
 				f = __viaddmax_s16x2(f, M2, tup);
@@ -140,7 +151,7 @@ struct StripS16 {
 
 			if (lane == (vo >> 1)) {
 				const int oc = (vo & 1) ? col_hi : col_lo;
-				if (!CHECK || (oc >= c0 && oc < c1)) sm.bot[warp][oc & 63] = make_uint2(oh, of);   // halves are picked at flush time
+				if (!CHECK || (oc >= c0 && oc < c1)) sm.bot[oc & 63] = make_uint2(oh, of);   // halves are picked at flush time
 			}
 			if (TRACK) {
 				bool plo, phi;
@@ -180,7 +191,7 @@ struct StripS16 {
 				if (s.ncand + n > kCand) drain(jb, s, sm, warp, lane, c0, c1);
 				if (trig) {
 					const int slot = s.ncand + __popc(mask & ((1u << lane) - 1u));
-					unsigned* e = sm.cand[warp][slot];
+					unsigned* e = sm.cand[slot];
 #pragma unroll
 					for (int r = 0; r < R; r++) e[r] = s.T[r];
 					e[R] = (unsigned)t;
@@ -219,7 +230,7 @@ struct StripS16 {
 
 	__device__ __forceinline__ static void drain(const StripJob& jb, State& s, Smem& sm, int warp, int lane, int c0, int c1) {
 		Best b; b.bs = s.bs; b.bi = s.bi; b.bj = s.bj;
-		b = drain_scan(sm.cand[warp], s.ncand, jb.rows, c0, c1, jb.i0, jb.j0, s.base, lane, b);
+		b = drain_scan(sm.cand, s.ncand, jb.rows, c0, c1, jb.i0, jb.j0, s.base, lane, b);
 		s.bs = b.bs; s.bi = b.bi; s.bj = b.bj;
 		s.ncand = 0;
 		const int wb = __reduce_max_sync(0xffffffffu, s.bs);
@@ -235,14 +246,14 @@ struct StripS16 {
 			s.E[r] = dup2(kNeg);
 		}
 		s.tprev = dup2(-kGapFirst);
-		s.botH = 0; s.botF = 0; s.pa = 0x02020202u; s.pb = 0x02020202u;
+		s.botH = 0; s.botF = 0; s.pa = LUT ? 0u : 0x02020202u; s.pb = s.pa;
 		s.Zp = 0;
 		s.thrp = thr_pack(s.thr, 0);
 		s.blk = 0x80008000u;
 	}
 
 	template <bool PARTIAL>
-	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane) {
+	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane, unsigned lut_addr = 0) {
 		const StripJob jb = p.jobs[job];
 		const int rows = jb.rows, cols = jb.cols, i0 = jb.i0, j0 = jb.j0;
 		const int rb_lo = (2 * lane) * R, rb_hi = (2 * lane + 1) * R;     // first row of each half inside the strip
@@ -255,6 +266,7 @@ struct StripS16 {
 		const int rows_left = p.prune_i1 - i0;                            // rows from the top of this strip to the end
 
 		State s;
+		s.lut = lut_addr + 4u * (unsigned)lane;
 		if (!lz) wait_left(p, jb.left_off + rows, lane);
 		// ---- left border; the frame starts at the H of the corner
 		const Cell* lb = p.left + jb.left_off;
@@ -278,7 +290,8 @@ struct StripS16 {
 			} else { hh = kNeg; }
 			s.T[r] = pack2(clamp16(hl), clamp16(hh));
 			s.E[r] = pack2(el, eh);
-			s.sel[r] = (unsigned)cl | ((unsigned)(8 | cl) << 4) | ((unsigned)(4 + chh) << 8) | ((unsigned)(12 + chh) << 12);
+			if (LUT) s.sel[r] = (unsigned)(cl | (chh << 2)) << 7;       // byte offset of table row cq inside a dq block (32 lanes x 4 B)
+			else s.sel[r] = (unsigned)cl | ((unsigned)(8 | cl) << 4) | ((unsigned)(4 + chh) << 8) | ((unsigned)(12 + chh) << 12);
 		}
 		{
 			// diagonal term of row 0 of each half at its first column: H(row above, column -1) - 5
@@ -289,7 +302,7 @@ struct StripS16 {
 			}
 			s.tprev = pack2(dl, dh);
 		}
-		s.botH = 0; s.botF = 0; s.pa = 0x02020202u; s.pb = 0x02020202u;
+		s.botH = 0; s.botF = 0; s.pa = LUT ? 0u : 0x02020202u; s.pb = s.pa;
 		s.Zp = dup2(clamp16(-base));
 		s.bs = INT_MIN; s.bi = -1; s.bj = -1; s.thr = INT_MIN; s.pub = INT_MIN; s.thrp = 0x80008000u; s.ncand = 0;
 		s.blk = 0x80008000u;
@@ -380,15 +393,15 @@ struct StripS16 {
 						if (s.thr != INT_MIN && bm1 != INT_MIN && bound < (long long)s.thr) c1 = tb;
 					}
 					if (tb < c1) {
-						int th = kNeg, tf = kNeg; unsigned pw = 0x02020202u;
+						int th = kNeg, tf = kNeg; unsigned pw = LUT ? 0u : 0x02020202u;
 						if (c < cols) {
 							th = tv.h < -kInf / 2 ? kNeg : clamp16(tv.h - s.base);
 							tf = tv.x < -kInf / 2 ? kNeg : clamp16(tv.x - s.base);
-							pw = profile_word(p.s1[j0 + c]);              // byte k = 6 (match+5) for the column's base, others 2 (mismatch+5)
+							pw = LUT ? (unsigned)code_of(p.s1[j0 + c]) : profile_word(p.s1[j0 + c]);   // column code, or profile word: byte k = 6 (match+5) / 2
 						}
-						sm.topH[warp][lane] = (unsigned)th << 16;
-						sm.topF[warp][lane] = (unsigned)tf << 16;
-						sm.prof[warp][lane] = pw;
+						sm.topH[lane] = (unsigned)th << 16;
+						sm.topF[lane] = (unsigned)tf << 16;
+						sm.prof[lane] = pw;
 						__syncwarp();
 					}
 				}
@@ -418,7 +431,7 @@ struct StripS16 {
 				if (cdone >= flushed) {
 					__syncwarp();
 					for (int c = flushed + lane; c <= cdone; c += 32) {
-						const uint2 pv = sm.bot[warp][c & 63];
+						const uint2 pv = sm.bot[c & 63];
 						const int vx = (vo & 1) ? hi16(pv.x) : lo16(pv.x), vy = (vo & 1) ? hi16(pv.y) : lo16(pv.y);
 						const int hv = vx <= kNeg ? -kInf : vx + s.base, fv = vy <= kNeg ? -kInf : vy + s.base;
 						stcg_cell(p.busH + j0 + c, hv, fv);
@@ -464,15 +477,29 @@ struct StripS16 {
 	}
 };
 
-// MIXED: the launch also contains JOB_S32 strips (rows with N / IUPAC bytes); pure A/C/G/T launches use the lean
-// instantiation (fewer registers, smaller code).
+// MIXED: the launch also contains JOB_S32 strips (rows with N / IUPAC bytes) and columns may hold such bytes: PRMT
+// variant plus the int32 path.  Pure A/C/G/T launches of the whole-partition instance (R = kR16F) use the LUT variant.
 template <int R, bool SW, bool TRACK, bool MIXED = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 12) strip_kernel_s16(const StripParams p) {
-	using K = StripS16<R, SW, TRACK>;
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) strip_kernel_s16(const StripParams p) {
+	constexpr bool LUT = !MIXED && R == kR16F;
+	using K = StripS16<R, SW, TRACK, LUT>;
 	using K32 = StripS32<16, SW, TRACK>;
-	__shared__ union { typename K::Smem s16; typename K32::Smem s32; } smu;
-	typename K::Smem& sm = smu.s16;
+	__shared__ union { typename K::Smem s16; typename K32::Smem s32; } smu[kWarpsPerBlock];   // per warp: warps run different job kinds
+	__shared__ unsigned lut[LUT ? 256 * 32 : 1];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	typename K::Smem& sm = smu[warp].s16;
+	unsigned lut_addr = 0;
+	if (LUT) {
+		// lut[dq*16 + cq][lane]: scores (+5) of row codes cq = c_lo | c_hi<<2 against column codes dq = d_lo | d_hi<<2
+		for (int idx = threadIdx.x; idx < 256 * 32; idx += blockDim.x) {
+			const int e = idx >> 5, cq = e & 15, dq = e >> 4;
+			const int lo = ((cq & 3) == (dq & 3)) ? kMatch + kGapFirst : kMismatch + kGapFirst;
+			const int hi = ((cq >> 2) == (dq >> 2)) ? kMatch + kGapFirst : kMismatch + kGapFirst;
+			lut[idx] = (unsigned)lo | ((unsigned)hi << 16);
+		}
+		__syncthreads();
+		lut_addr = (unsigned)__cvta_generic_to_shared(lut);
+	}
 	for (;;) {
 		int job = 0;
 		if (lane == 0) job = atomicAdd(p.job_counter, 1);
@@ -491,9 +518,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 12) strip_kernel_s16(cons
 			if (lane == 0) { __threadfence(); st_release(p.progress + job, jb.cols); }
 			continue;
 		}
-		if (MIXED && (flags & JOB_S32)) K32::run_job(p, job, smu.s32, warp, lane);      // rows with N / IUPAC bytes: exact int32 path
-		else if (rows < K::SH) K::template run_job<true>(p, job, sm, warp, lane);
-		else K::template run_job<false>(p, job, sm, warp, lane);
+		if (MIXED && (flags & JOB_S32)) K32::run_job(p, job, smu[warp].s32, warp, lane);      // rows with N / IUPAC bytes: exact int32 path
+		else if (rows < K::SH) K::template run_job<true>(p, job, sm, warp, lane, lut_addr);
+		else K::template run_job<false>(p, job, sm, warp, lane, lut_addr);
 	}
 }
 

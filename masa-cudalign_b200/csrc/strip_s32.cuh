@@ -13,7 +13,7 @@
 
 namespace b200 {
 
-constexpr int kWarpsPerBlock = 1;   // one strip-warp per CTA: resident warps per SM can be any number up to the register limit
+constexpr int kWarpsPerBlock = 4;   // strip-warps per CTA: they only share the 32 KB substitution table of the packed kernel
 
 template <int R, bool SW, bool TRACK>
 struct StripS32 {
@@ -21,9 +21,9 @@ struct StripS32 {
 	static constexpr int SH = V * R;      // strip height
 
 	struct Smem {
-		Cell top[kWarpsPerBlock][32];
-		Cell bot[kWarpsPerBlock][64];
-		unsigned char seq[kWarpsPerBlock][32];
+		Cell top[32];
+		Cell bot[64];
+		unsigned char seq[32];
 	};
 
 	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane) {
@@ -84,8 +84,8 @@ struct StripS32 {
 					if (!top_minf) tv = ldcg_cell(p.busH + j0 + c);
 					ch = p.s1[j0 + c];
 				}
-				sm.top[warp][lane] = tv;
-				sm.seq[warp][lane] = ch;
+				sm.top[lane] = tv;
+				sm.seq[lane] = ch;
 				if (TRACK && p.track == 2) {
 					if (thr > pub) { if (lane == 0) push_best(p, thr); pub = thr; }
 					const int g = ld_uniform(p.global_best);
@@ -100,8 +100,8 @@ struct StripS32 {
 				int upH = __shfl_up_sync(0xffffffffu, botH, 1);
 				int upF = __shfl_up_sync(0xffffffffu, botF, 1);
 				int cc = __shfl_up_sync(0xffffffffu, ccur, 1);
-				const Cell tv = sm.top[warp][u];
-				const int tc = sm.seq[warp][u];
+				const Cell tv = sm.top[u];
+				const int tc = sm.seq[u];
 				if (lane == 0) { upH = tv.h; upF = tv.x; cc = tc; }
 				ccur = cc;
 				const int col = t - lane;
@@ -127,7 +127,7 @@ struct StripS32 {
 					}
 					if (!partial) { oh = h; of = f; }
 					botH = h; botF = f;
-					if (lane == vo) { Cell o; o.h = oh; o.x = of; sm.bot[warp][col & 63] = o; }
+					if (lane == vo) { Cell o; o.h = oh; o.x = of; sm.bot[col & 63] = o; }
 					if (TRACK) trig = smax >= thr;
 					if (col == cols - 1 && jb.right_off >= 0) {
 						Cell* rb = p.right + jb.right_off;
@@ -159,7 +159,7 @@ struct StripS32 {
 			if (cdone >= flushed) {
 				__syncwarp();
 				for (int c = flushed + lane; c <= cdone; c += 32) {
-					const Cell v = sm.bot[warp][c & 63];
+					const Cell v = sm.bot[c & 63];
 					stcg_cell(p.busH + j0 + c, v.h, v.x);
 					if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, v.h, v.x);
 				}
@@ -193,8 +193,9 @@ struct StripS32 {
 template <int R, bool SW, bool TRACK>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) strip_kernel_s32(const StripParams p) {
 	using K = StripS32<R, SW, TRACK>;
-	__shared__ typename K::Smem sm;
+	__shared__ typename K::Smem smw[kWarpsPerBlock];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	typename K::Smem& sm = smw[warp];
 	for (;;) {
 		int job = 0;
 		if (lane == 0) job = atomicAdd(p.job_counter, 1);
