@@ -480,7 +480,7 @@ struct StripS16 {
 // MIXED: the launch also contains JOB_S32 strips (rows with N / IUPAC bytes) and columns may hold such bytes: PRMT
 // variant plus the int32 path.  Pure A/C/G/T launches of the whole-partition instance (R = kR16F) use the LUT variant.
 template <int R, bool SW, bool TRACK, bool MIXED = false>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) strip_kernel_s16(const StripParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) strip_kernel_s16(const StripParams p) {
 	constexpr bool LUT = !MIXED && R == kR16F;
 	using K = StripS16<R, SW, TRACK, LUT>;
 	using K32 = StripS32<16, SW, TRACK>;
