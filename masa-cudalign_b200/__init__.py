@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb200align.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libb200align.so")   # B200_LIB: development builds of the same library
 
 INF = 999999999
 NEEDLEMAN_WUNSCH, SMITH_WATERMAN = 0, 1                          # C/libmasa/IManager.hpp:31-33

@@ -184,9 +184,16 @@ __global__ void match_column_kernel(const Cell* buffer, const Cell* base, int le
 // strip above it), so the grid never exceeds SMs x occupancy.  Below that limit the number of resident warps
 // per SM is chosen so that the strips fill whole waves: every strip sweeps the full width at the pace of one
 // warp, so a last, nearly empty wave would cost as much as a full one.  kSatWarps: resident strip-warps per SM
-// beyond which the measured throughput no longer grows (ALU pipe ~75% busy in steady state, profiles/r01_*):
-// more warps only stretch each wave.
-constexpr int kSatWarps = 11;
+// beyond which the measured throughput no longer grows.  With the LUT kernel the rate still grows up to the 16
+// warps that fit (5M x 5M without pruning: 4083 GCUPS at 11 warps/SM, 4426 at 16; profiles/r01_protocol_options.txt).
+constexpr int kSatWarps = 16;
+// protocol variant of the strip chain (StripOpt bits); B200_OPT overrides the default for experiments
+constexpr int kDefaultStripOpt = OPT_NO_SC_FENCE | OPT_SEEN_CACHE | OPT_RELEASE_128 | OPT_BEST_EVERY_4 | OPT_SKIP_128;   // measured: profiles/r01_protocol_options.txt
+int strip_opt() {
+	const char* e = getenv("B200_OPT");      // read per launch: experiments switch it between runs of one process
+	return e ? atoi(e) : kDefaultStripOpt;
+}
+
 int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 	int per_sm = 0;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, 0);
@@ -230,6 +237,7 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.recurrence = recurrence;
 	sp.track = track;
 	sp.prune = h->ov.prune; sp.prune_i1 = h->ov.prune_i1; sp.prune_j1 = h->ov.prune_j1;
+	sp.opt = strip_opt();
 	const bool sw = recurrence == B200_SMITH_WATERMAN;
 	const void* fn = nullptr;
 	if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F && h->ov.mixed) {

@@ -69,6 +69,16 @@ struct StripParams {
 	int track;              // 0: no best tracking; 1: exact best cell per job; 2: per job, thresholded by global_best
 	int prune;              // SW block pruning inside the strips (needs track == 2)
 	int prune_i1, prune_j1; // end of the (super) partition: bounds of the distance term of the pruning test
+	int opt;                // StripOpt bits: protocol variants of the strip chain (engine default, B200_OPT overrides)
+};
+
+// Variants of the strip-chaining protocol (all exact; they only change how often the chain synchronises).
+enum StripOpt : int {
+	OPT_NO_SC_FENCE   = 1,   // publish with st.release.gpu alone (no extra fence.sc in front of it)
+	OPT_SEEN_CACHE    = 2,   // remember the last progress value observed: no acquire while it covers the next block
+	OPT_RELEASE_128   = 4,   // after the first 2048 columns release the progress counter every 128 columns, not every 32
+	OPT_BEST_EVERY_4  = 8,   // exchange the running best with global_best every 4th block
+	OPT_SKIP_128      = 16,  // skip mode decides 128 columns at a time when the strip above is that far ahead
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
@@ -106,6 +116,19 @@ __device__ __forceinline__ void wait_progress(const StripParams& p, int dep, int
 		}
 	}
 	__syncwarp();
+}
+// same, returning the progress value observed (warp-uniform) so that the caller can skip later waits it already covers
+__device__ __forceinline__ int wait_progress_v(const StripParams& p, int dep, int need, int lane) {
+	int v = 0;
+	if (lane == 0) {
+		unsigned spins = 0;
+		while ((v = ld_acquire(p.progress + dep)) < need) {
+			if (ld_relaxed(p.stop_flag)) break;
+			if (++spins > kSpinLimit) { atomicExch(p.stop_flag, 2); break; }
+			__nanosleep(64);
+		}
+	}
+	return __shfl_sync(0xffffffffu, v, 0);
 }
 __device__ __forceinline__ void wait_left(const StripParams& p, int upto, int lane) {
 	if (p.left_ready == nullptr) return;

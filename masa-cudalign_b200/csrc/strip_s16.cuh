@@ -35,6 +35,14 @@
 
 namespace b200 {
 
+// unroll factor of the check-free wavefront loop: the loop-carried registers of one step do not map onto themselves,
+// so every trip around the loop ends in a block of register moves; unrolling amortises them (2: 175, 4: 163.5,
+// 8: 157 instructions per step, tools/sass_step_count.py)
+#ifndef B200_STEP_UNROLL
+#define B200_STEP_UNROLL 4
+#endif
+constexpr int kStepUnroll = B200_STEP_UNROLL;
+
 constexpr int kR16 = 8;                 // diag-compat instance: 64*8  = 512-row strips (reference block height)
 constexpr int kSH16 = 64 * kR16;
 constexpr int kR16F = 16;               // whole-partition instance: 64*16 = 1024-row strips
@@ -84,10 +92,12 @@ struct StripS16 {
 	static constexpr int SH = V * R;
 
 	struct Smem {
-		unsigned topH[32];   // H<<16 of the top border in the local frame (lane 0 injects it into its low half)
-		unsigned topF[32];   // F<<16
-		unsigned prof[32];   // column profile words: byte k = s(k, column base) + 5
-		uint2 bot[64];       // packed (H,F) registers of the lane that owns the bottom row, ring over columns
+		// per column of the current 32-column block: {H<<16, F<<16 of the top border in the local frame (lane 0 injects
+		// them into its low half), column profile word (byte k = s(k, column base) + 5) or LUT row offset (code << 11)}:
+		// one LDS.128 per step
+		uint4 top[32];
+		unsigned botH[32];   // packed H / F registers of the lane that owns the bottom row, indexed by the step inside the
+		unsigned botF[32];   // block: step u completes column (block start + u - vo) of the bottom row
 		unsigned cand[kCand][R + 2];   // deferred best-cell candidates: T[0..R) of a lane + {step, lane|halves<<8}
 	};
 
@@ -108,27 +118,28 @@ struct StripS16 {
 		unsigned shH = __shfl_up_sync(0xffffffffu, s.botH, 1);
 		unsigned shF = __shfl_up_sync(0xffffffffu, s.botF, 1);
 		unsigned shP = __shfl_up_sync(0xffffffffu, s.pb, 1);
-		if (lane == 0) { shH = sm.topH[u]; shF = sm.topF[u]; shP = sm.prof[u]; }   // predicated LDS, no SEL
+		if (lane == 0) { const uint4 tp = sm.top[u]; shH = tp.x; shF = tp.y; shP = tp.z; }   // one predicated LDS.128
 		const unsigned upH = prmt(shH, s.botH, 0x5432);      // lo <- neighbour's hi, hi <- own lo
 		const unsigned upF = prmt(shF, s.botF, 0x5432);
 		s.pb = s.pa; s.pa = shP;
 		const int col_lo = t - 2 * lane, col_hi = col_lo - 1;
 		bool act = true;
 		if (CHECK) act = (col_lo >= c0) && (col_hi < c1);           // at least one half inside the segment [c0, c1)
-		bool trig = false, trig_lo = false, trig_hi = false;
+		bool trig = false;
+		unsigned smax_out = 0x80008000u;
+		unsigned keep = 0;                                            // halves to freeze (CHECK): 0xffff lo, 0xffff0000 hi
 		if (act) {
 			unsigned dT = s.tprev;
 			unsigned tup = __vadd2(upH, M5);
 			unsigned f = upF, h = 0, smax = dup2(-32768), oh = 0, of = 0;
 			// during fill/drain one half may be outside [0, cols): its state must not move
-			unsigned keep = 0;                                        // halves to freeze: 0xffff lo, 0xffff0000 hi
 			if (CHECK) {
 				if (col_lo >= c1) keep |= 0x0000ffffu;
 				if (col_hi < c0) keep |= 0xffff0000u;
 			}
 			s.tprev = CHECK ? ((tup & ~keep) | (s.tprev & keep)) : tup;
 			unsigned lrow = 0;
-			if (LUT) lrow = s.lut + ((s.pa | (s.pb << 2)) << 11);      // table rows of this step's two column codes
+			if (LUT) lrow = s.lut + s.pa + (s.pb << 2);                // table rows of this step's two column codes (pa, pb = code << 11)
 #pragma unroll
 			for (int r = 0; r < R; r++) {
 				unsigned sc;
@@ -151,18 +162,19 @@ struct StripS16 {
 
 			if (lane == (vo >> 1)) {
 				const int oc = (vo & 1) ? col_hi : col_lo;
-				if (!CHECK || (oc >= c0 && oc < c1)) sm.bot[oc & 63] = make_uint2(oh, of);   // halves are picked at flush time
+				if (!CHECK || (oc >= c0 && oc < c1)) { sm.botH[u] = oh; sm.botF[u] = of; }   // halves are picked at flush time
 			}
 			if (TRACK) {
-				bool plo, phi;
-				(void)__vibmax_s16x2(smax, s.thrp, &phi, &plo);
-				trig_lo = plo; trig_hi = phi;
 				if (CHECK) {
 					// frozen halves carry stale values: they feed neither the trigger nor the pruning maximum
-					if (keep & 0x0000ffffu) { trig_lo = false; smax = (smax & 0xffff0000u) | 0x8000u; }
-					if (keep & 0xffff0000u) { trig_hi = false; smax = (smax & 0x0000ffffu) | 0x80000000u; }
+					if (keep & 0x0000ffffu) smax = (smax & 0xffff0000u) | 0x8000u;
+					if (keep & 0xffff0000u) smax = (smax & 0x0000ffffu) | 0x80000000u;
 				}
-				trig = trig_lo || trig_hi;
+				bool plo, phi;
+				(void)__vibmax_s16x2(smax, s.thrp, &phi, &plo);
+				if (CHECK) { if (keep & 0x0000ffffu) plo = false; if (keep & 0xffff0000u) phi = false; }
+				trig = plo || phi;
+				smax_out = smax;
 				s.blk = __vmaxs2(s.blk, smax);
 			}
 			if (CHECK && jb.right_off >= 0) {
@@ -190,12 +202,18 @@ struct StripS16 {
 				const int n = __popc(mask);
 				if (s.ncand + n > kCand) drain(jb, s, sm, warp, lane, c0, c1);
 				if (trig) {
+					// which halves reached the threshold is recomputed here (opaque copy: no flag registers on the hot path)
+					unsigned sx = smax_out;
+					asm volatile("" : "+r"(sx));
+					bool plo, phi;
+					(void)__vibmax_s16x2(sx, s.thrp, &phi, &plo);
+					if (CHECK) { if (keep & 0x0000ffffu) plo = false; if (keep & 0xffff0000u) phi = false; }
 					const int slot = s.ncand + __popc(mask & ((1u << lane) - 1u));
 					unsigned* e = sm.cand[slot];
 #pragma unroll
 					for (int r = 0; r < R; r++) e[r] = s.T[r];
 					e[R] = (unsigned)t;
-					e[R + 1] = (unsigned)lane | (trig_lo ? 0x100u : 0u) | (trig_hi ? 0x200u : 0u);
+					e[R + 1] = (unsigned)lane | (plo ? 0x100u : 0u) | (phi ? 0x200u : 0u);
 				}
 				s.ncand += n;
 			}
@@ -206,16 +224,23 @@ struct StripS16 {
 
 	// Cooperative scan of the candidate ring: lane l examines cell (half = l / R, row = l % R) of every entry.
 	// Takes and returns scalars only, so the register-resident State never has its address taken.
-	__device__ __noinline__ static Best drain_scan(const unsigned (*cand)[R + 2], int ncand, int rows, int c0, int c1, int i0, int j0,
+	// `cand` is the 32-bit shared-memory address of the ring: a generic pointer argument would have its 64-bit address
+	// materialised in the hot loop of the caller
+	__device__ __forceinline__ static unsigned lds32(unsigned addr) {
+		unsigned v;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+		return v;
+	}
+	__device__ __noinline__ static Best drain_scan(unsigned cand, int ncand, int rows, int c0, int c1, int i0, int j0,
 	                                               int base, int lane, Best b) {
 		__syncwarp();
 		const int half = lane / R, r = lane % R;
 		for (int e = 0; e < ncand; e++) {
-			const unsigned* en = cand[e];
-			const unsigned meta = en[R + 1];
-			const int te = (int)en[R], src = (int)(meta & 31u);
+			const unsigned en = cand + (unsigned)e * (R + 2) * 4u;
+			const unsigned meta = lds32(en + (R + 1) * 4u);
+			const int te = (int)lds32(en + R * 4u), src = (int)(meta & 31u);
 			if (half < 2 && ((meta >> (8 + half)) & 1u)) {
-				const unsigned w = en[r];
+				const unsigned w = lds32(en + (unsigned)r * 4u);
 				const int v = 2 * src + half, col = te - v, row = v * R + r;
 				if (row < rows && col >= c0 && col < c1) {
 					const int hv = (half ? hi16(w) : lo16(w)) + kGapFirst + base;
@@ -230,7 +255,7 @@ struct StripS16 {
 
 	__device__ __forceinline__ static void drain(const StripJob& jb, State& s, Smem& sm, int warp, int lane, int c0, int c1) {
 		Best b; b.bs = s.bs; b.bi = s.bi; b.bj = s.bj;
-		b = drain_scan(sm.cand, s.ncand, jb.rows, c0, c1, jb.i0, jb.j0, s.base, lane, b);
+		b = drain_scan((unsigned)__cvta_generic_to_shared(&sm.cand[0][0]), s.ncand, jb.rows, c0, c1, jb.i0, jb.j0, s.base, lane, b);
 		s.bs = b.bs; s.bi = b.bi; s.bj = b.bj;
 		s.ncand = 0;
 		const int wb = __reduce_max_sync(0xffffffffu, s.bs);
@@ -267,6 +292,7 @@ struct StripS16 {
 
 		State s;
 		s.lut = lut_addr + 4u * (unsigned)lane;
+		asm volatile("mov.u32 %0, %0;" : "+r"(s.lut));          // opaque: keep it in a register instead of re-deriving it every step
 		if (!lz) wait_left(p, jb.left_off + rows, lane);
 		// ---- left border; the frame starts at the H of the corner
 		const Cell* lb = p.left + jb.left_off;
@@ -308,6 +334,8 @@ struct StripS16 {
 		s.blk = 0x80008000u;
 
 		int flushed = 0;                       // columns of the bottom row published so far (computed or skipped)
+		int seen = jb.dep < 0 ? INT_MAX : 0;   // progress of the strip above observed by our last acquire (OPT_SEEN_CACHE)
+		const int opt = p.opt;
 		int pos = 0;                           // next column to decide in skip mode
 		bool computing = !(prune && lz);       // a zero left border lets the strip start in skip mode
 		long long computed_cols = 0;
@@ -318,10 +346,36 @@ struct StripS16 {
 				// =========================== SKIP mode: one 32-column block per iteration ===========================
 				if (pos >= cols) break;
 				const int need = pos + 32 < cols ? pos + 32 : cols;
-				wait_progress(p, jb.dep, need, lane);
-				if (p.track == 2) {
+				if (!(opt & OPT_SEEN_CACHE)) wait_progress(p, jb.dep, need, lane);
+				else if (seen < need) seen = wait_progress_v(p, jb.dep, need, lane);
+				if (p.track == 2 && (!(opt & OPT_BEST_EVERY_4) || (pos & 96) == 0)) {
 					const int g = ld_uniform(p.global_best);
 					if (g > s.thr) { s.thr = g; s.pub = g; }
+				}
+				if ((opt & OPT_SKIP_128) && s.thr != INT_MIN && pos + 128 <= cols && seen >= pos + 128) {
+					// the strip above is at least 128 columns ahead: decide four blocks with one reduction, one burst of
+					// stores and one release (bound of the first block: the largest distance term, so never less strict)
+					int th = 0;
+					if (!top_minf) {
+						const Cell* tp = p.busH + j0 + pos + lane;
+						const int h0 = __ldcg(&tp[0].h), h1 = __ldcg(&tp[32].h), h2 = __ldcg(&tp[64].h), h3 = __ldcg(&tp[96].h);
+						th = max(max(h0, h1), max(h2, h3));
+					}
+					int tmax = __reduce_max_sync(0xffffffffu, th);
+					if (tmax < 0) tmax = 0;
+					const int cols_left = p.prune_j1 - (j0 + pos);
+					const long long bound = (long long)tmax + kPruneSlack + (rows_left < cols_left ? rows_left : cols_left);
+					if (bound < (long long)s.thr) {
+#pragma unroll
+						for (int k = 0; k < 4; k++) {
+							stcg_cell(p.busH + j0 + pos + lane + 32 * k, 0, -kInf);
+							if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + pos + lane + 32 * k, 0, -kInf);
+						}
+						pos += 128; flushed = pos;
+						__syncwarp();
+						if (lane == 0) { if (!(opt & OPT_NO_SC_FENCE)) __threadfence(); st_release(p.progress + job, flushed); }
+						continue;
+					}
 				}
 				const int c = pos + lane;
 				int th = 0;
@@ -337,7 +391,7 @@ struct StripS16 {
 					}
 					pos = need; flushed = need;
 					__syncwarp();
-					if (lane == 0) { __threadfence(); st_release(p.progress + job, flushed); }
+					if (lane == 0) { if (!(opt & OPT_NO_SC_FENCE)) __threadfence(); st_release(p.progress + job, flushed); }
 					continue;
 				}
 				start_zero_segment(s, nv_lo, nv_hi);
@@ -372,8 +426,9 @@ struct StripS16 {
 				// ---- stage the next 32 columns of top border and seq1 (coalesced), gated on the strip above
 				if (tb < c1) {
 					const int need = tb + 32 < cols ? tb + 32 : cols;
-					wait_progress(p, jb.dep, need, lane);
-					if (TRACK && p.track == 2) {
+					if (!(opt & OPT_SEEN_CACHE)) wait_progress(p, jb.dep, need, lane);
+					else if (seen < need) seen = wait_progress_v(p, jb.dep, need, lane);
+					if (TRACK && p.track == 2 && (!(opt & OPT_BEST_EVERY_4) || (tb & 96) == 0 || tb == c0)) {
 						// share the running best: publish ours, adopt a higher one (monotone, staleness is harmless)
 						if (s.thr > s.pub) { if (lane == 0) push_best(p, s.thr); s.pub = s.thr; }
 						const int g = ld_uniform(p.global_best);
@@ -397,11 +452,9 @@ struct StripS16 {
 						if (c < cols) {
 							th = tv.h < -kInf / 2 ? kNeg : clamp16(tv.h - s.base);
 							tf = tv.x < -kInf / 2 ? kNeg : clamp16(tv.x - s.base);
-							pw = LUT ? (unsigned)code_of(p.s1[j0 + c]) : profile_word(p.s1[j0 + c]);   // column code, or profile word: byte k = 6 (match+5) / 2
+							pw = LUT ? (unsigned)code_of(p.s1[j0 + c]) << 11 : profile_word(p.s1[j0 + c]);   // LUT row offset of the column code, or profile word: byte k = 6 (match+5) / 2
 						}
-						sm.topH[lane] = (unsigned)th << 16;
-						sm.topF[lane] = (unsigned)tf << 16;
-						sm.prof[lane] = pw;
+						sm.top[lane] = make_uint4((unsigned)th << 16, (unsigned)tf << 16, pw, 0u);
 						__syncwarp();
 					}
 				}
@@ -409,7 +462,7 @@ struct StripS16 {
 				// ---- 32 steps; the check-free body runs whenever every virtual lane is inside [c0, c1)
 				const bool steady = (tb >= c0 + V) && (tb + 32 < c1);
 				if (steady) {
-#pragma unroll 2
+#pragma unroll kStepUnroll
 					for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
 				} else {
 #pragma unroll 1
@@ -431,16 +484,21 @@ struct StripS16 {
 				if (cdone >= flushed) {
 					__syncwarp();
 					for (int c = flushed + lane; c <= cdone; c += 32) {
-						const uint2 pv = sm.bot[c & 63];
-						const int vx = (vo & 1) ? hi16(pv.x) : lo16(pv.x), vy = (vo & 1) ? hi16(pv.y) : lo16(pv.y);
+						const int k = c - tb + vo;                 // step of this block that completed column c of the bottom row
+						const unsigned px = sm.botH[k], py = sm.botF[k];
+						const int vx = (vo & 1) ? hi16(px) : lo16(px), vy = (vo & 1) ? hi16(py) : lo16(py);
 						const int hv = vx <= kNeg ? -kInf : vx + s.base, fv = vy <= kNeg ? -kInf : vy + s.base;
 						stcg_cell(p.busH + j0 + c, hv, fv);
 						if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, hv, fv);
 					}
+					// the strips below start as soon as the first columns are out; once the chain is filled the counter is
+					// released every 128 columns (a release costs a fence; the consumers run several blocks behind anyway)
+					const bool rel = !(opt & OPT_RELEASE_128) || cdone + 1 == cols || cdone < 2048 || tb + 32 >= c1 ||
+					                 ((cdone + 1) >> 7) != (flushed >> 7);
 					flushed = cdone + 1;
 					if (flushed == cols && jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
 					__syncwarp();
-					if (lane == 0) { __threadfence(); st_release(p.progress + job, flushed); }
+					if (rel && lane == 0) { if (!(opt & OPT_NO_SC_FENCE)) __threadfence(); st_release(p.progress + job, flushed); }
 				}
 			}
 			computed_cols += c1 - c0;

@@ -50,10 +50,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) step_rate_kernel(St
 	const int vo = (K::SH - 1) / R, ro = (K::SH - 1) % R;
 	for (int b = 0; b < blocks32; b++) {
 		x = x * 1664525u + 1013904223u;
-		sm.topH[lane] = 0; sm.topF[lane] = (unsigned)kNeg << 16;
-		sm.prof[lane] = LUT ? ((x >> 10) & 3u) : profile_word("ACGT"[(x >> 10) & 3u]);
+		sm.top[lane] = make_uint4(0u, (unsigned)kNeg << 16, LUT ? (((x >> 10) & 3u) << 11) : profile_word("ACGT"[(x >> 10) & 3u]), 0u);
 		__syncwarp();
-#pragma unroll 2
+#pragma unroll kStepUnroll
 		for (int u = 0; u < 32; u++)
 			K::template step<false, false>(p, jb, s, sm, warp, lane, 64 + b * 32 + u, u, R, R, vo, ro, 0, INT_MAX);
 		// keep the frame bounded like the rebase of the real kernel (cheap, every 32 steps)

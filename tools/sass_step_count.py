@@ -61,7 +61,7 @@ def main():
     R = args.rows_per_lane
     for s, e in loops:
         nv = sum(1 for _, t in ins[s:e + 1] if "VIADDMNMX" in t)
-        if nv < 3 * R or nv % (3 * R) or e - s > 1200:
+        if nv < 3 * R or nv % (3 * R) or e - s > 4000:
             continue
         steps = nv // (3 * R)
         # walk the fall-through path
