@@ -131,3 +131,32 @@ def test_mixed_alphabet_matches_byte_compare(b200):
     rp = al.align_partition(prune=True)
     assert rp["best"] == o["best"]
     al.close()
+
+
+@pytest.fixture(scope="module")
+def chain_case():
+    m, n = 70000, 40000                                       # 69 strips of 1024 rows, 1250 blocks each
+    a, b = synth.make_pair(m, n, [(4000, 60000)], 0.05, 0.01, 0.01, 0, 31)
+    ids = list(range(8192, m, 8192)) + [m]
+    return a, b, ids, O.full_matrix(a, b, O.SW, row_ids=[i - 1 for i in ids])   # the oracle runs once for all variants
+
+
+@pytest.mark.parametrize("opt", [0, 1, 2, 3, 7, 15, 27, 31])
+def test_chain_protocol_variants_are_exact(b200, opt, chain_case, monkeypatch):
+    """Every StripOpt combination (csrc/strip_common.cuh: fence choice, cached progress, 128-column releases, best
+    exchange every 4th block, 128-column skips) only changes how often the strip chain synchronises: results stay
+    bit-exact without pruning, and the best cell stays exact with pruning."""
+    a, b, ids, o = chain_case
+    monkeypatch.setenv("B200_OPT", str(opt))
+    al = b200.Aligner(kernel=b200.KERNEL_S16X2)
+    al.set_sequences(a, b)
+    r = al.align_partition(want_last_row=True, want_last_column=True, want_special_rows=True, special_row_interval=1000)
+    assert sorted(r["rows"]) == ids
+    assert r["best"] == o["best"]
+    for i in ids:
+        assert np.array_equal(r["rows"][i], o["rows"][i - 1]), f"row {i}"
+    assert np.array_equal(r["last_column"], o["last_col"])
+    rp = al.align_partition(prune=True)
+    assert rp["best"] == o["best"]
+    assert rp["cells"] < r["cells"]
+    al.close()
