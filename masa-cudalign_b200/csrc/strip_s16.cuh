@@ -51,6 +51,7 @@ constexpr int kSH16F = 64 * kR16F;
 constexpr int kNeg = -30000;            // local-frame stand-in for -INF
 constexpr int kRebase = 4096;           // re-centre when |reference cell| exceeds this
 constexpr int kCand = 32;               // candidate-ring entries per warp (>= 32: one step can trigger every lane)
+constexpr int kFiltMin = 128;            // FILT steps only above this best score: random DNA reaches H ~ 30-40, so the F-chain bound (+33) stays below it
 constexpr int kPruneSlack = 66;         // growth possible while the 64-lane pipeline drains, plus rounding
 
 __device__ __forceinline__ unsigned pack2(int lo, int hi) { return ((unsigned)lo & 0xffffu) | ((unsigned)hi << 16); }
@@ -111,7 +112,12 @@ struct StripS16 {
 		int bs, bi, bj, thr, pub, ncand;
 	};
 
-	template <bool PARTIAL, bool CHECK>
+	// FILT (check-free steps of a tracking kernel, once the best known score is >= kFiltMin): the per-row running
+	// maximum (R/2 VIMNMX3 per step) is replaced by ONE conservative bound taken from the F chain.  Inside a lane-step
+	// F(r) >= H(k) - 5 - 2(r-1-k) for every row k < r, so  max_k H(k) <= max(F(R-1) + 2R + 1, H(R-1)).  Only when that
+	// bound reaches the threshold (rows just below a high-scoring cell) is the exact maximum taken from the T registers,
+	// on the rare path.  The bound also feeds the pruning maximum, where an upper bound is all that is needed.
+	template <bool PARTIAL, bool CHECK, bool FILT = false>
 	__device__ __forceinline__ static void step(const StripParams& p, const StripJob& jb, State& s, Smem& sm, int warp, int lane,
 	                                            int t, int u, int nv_lo, int nv_hi, int vo, int ro, int c0, int c1) {
 		const unsigned M2 = dup2(-kGapExt), M5 = dup2(-kGapFirst);
@@ -153,9 +159,10 @@ struct StripS16 {
 				tup = __vadd2(h, M5);
 				if (CHECK) { s.E[r] = (e & ~keep) | (s.E[r] & keep); s.T[r] = (tup & ~keep) | (s.T[r] & keep); }
 				else { s.E[r] = e; s.T[r] = tup; }
-				if (TRACK) smax = __vmaxs2(smax, h);
+				if (TRACK && !FILT) smax = __vmaxs2(smax, h);
 				if (PARTIAL && r == ro) { oh = h; of = f; }
 			}
+			if (TRACK && FILT) smax = __viaddmax_s16x2(f, dup2(2 * R + 1), h);
 			if (!PARTIAL) { oh = h; of = f; }
 			if (CHECK) { s.botH = (h & ~keep) | (s.botH & keep); s.botF = (f & ~keep) | (s.botF & keep); }
 			else { s.botH = h; s.botF = f; }
@@ -197,7 +204,19 @@ struct StripS16 {
 			// H registers in the warp's candidate ring (a handful of STS); the exact (score,i,j) bookkeeping is done
 			// by all 32 lanes together in drain(), every 32 columns, so the strip that carries the alignment path
 			// does not throttle the strips chained below it.
-			const unsigned mask = __ballot_sync(0xffffffffu, trig);
+			unsigned mask = __ballot_sync(0xffffffffu, trig);
+			if (FILT && mask) {
+				// some lane's bound reached the threshold: exact maximum of this step's H values from the T registers
+				unsigned tm = s.T[0];
+#pragma unroll
+				for (int r = 1; r + 1 < R; r += 2) tm = __vimax3_s16x2(tm, s.T[r], s.T[r + 1]);
+				if ((R & 1) == 0) tm = __vmaxs2(tm, s.T[R - 1]);
+				smax_out = __vadd2(tm, dup2(kGapFirst));
+				bool plo, phi;
+				(void)__vibmax_s16x2(smax_out, s.thrp, &phi, &plo);
+				trig = trig && (plo || phi);
+				mask = __ballot_sync(0xffffffffu, trig);
+			}
 			if (mask) {
 				const int n = __popc(mask);
 				if (s.ncand + n > kCand) drain(jb, s, sm, warp, lane, c0, c1);
@@ -461,7 +480,10 @@ struct StripS16 {
 
 				// ---- 32 steps; the check-free body runs whenever every virtual lane is inside [c0, c1)
 				const bool steady = (tb >= c0 + V) && (tb + 32 < c1);
-				if (steady) {
+				if (steady && TRACK && s.thr >= kFiltMin) {
+#pragma unroll kStepUnroll
+					for (int u = 0; u < 32; u++) step<PARTIAL, false, true>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
+				} else if (steady) {
 #pragma unroll kStepUnroll
 					for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
 				} else {

@@ -61,9 +61,9 @@ def main():
     R = args.rows_per_lane
     for s, e in loops:
         nv = sum(1 for _, t in ins[s:e + 1] if "VIADDMNMX" in t)
-        if nv < 3 * R or nv % (3 * R) or e - s > 4000:
-            continue
         steps = nv // (3 * R)
+        if nv < 3 * R or nv % (3 * R) not in (0, steps) or e - s > 4000:      # + 1 per step: the F-chain bound of the FILT variant
+            continue
         # walk the fall-through path
         i, path = s, []
         while i <= e:
