@@ -281,18 +281,27 @@ struct StripS16 {
 		if (wb > s.thr) { s.thr = wb; s.thrp = thr_pack(s.thr, s.base); }
 	}
 
-	// (re)start a compute segment whose left neighbour is all zeros (SW): H = 0, E = -INF
-	__device__ __forceinline__ static void start_zero_segment(State& s, int nv_lo, int nv_hi) {
-		s.base = 0;
+	// (re)start a compute segment whose left neighbour is all zeros (SW): H = 0, E = -INF.
+	// The frame is taken from the TOP border the segment starts under (tmax = its largest H): in the lower part of a
+	// large matrix the surviving band starts at cells worth millions (reached from the alignment path through long
+	// gaps), and a frame anchored at zero would saturate the s16 lanes for tmax/32767 blocks while re-centring catches
+	// up -- under-estimated cells that the strips below inherit, a front that creeps towards the alignment path by
+	// (tmax/1024 - strip shift) columns per strip and finally erases it (seen on the 23M x 25M pair: best lost after row
+	// 20.9M).  With the frame at the top border the zeros on the left become the frame's floor, like every SW zero once
+	// base > 30000; they are dead cells by the pruning bound, far below every live value.
+	__device__ __forceinline__ static void start_zero_segment(State& s, int nv_lo, int nv_hi, int tmax) {
+		const int b = tmax > 16384 ? tmax - 8192 : 0;
+		const int z = clamp16(-b), t0 = clamp16(-b - kGapFirst);
+		s.base = b;
 #pragma unroll
 		for (int r = 0; r < R; r++) {
-			s.T[r] = pack2(r < nv_lo ? -kGapFirst : kNeg, r < nv_hi ? -kGapFirst : kNeg);
+			s.T[r] = pack2(r < nv_lo ? t0 : kNeg, r < nv_hi ? t0 : kNeg);
 			s.E[r] = dup2(kNeg);
 		}
-		s.tprev = dup2(-kGapFirst);
-		s.botH = 0; s.botF = 0; s.pa = LUT ? 0u : 0x02020202u; s.pb = s.pa;
-		s.Zp = 0;
-		s.thrp = thr_pack(s.thr, 0);
+		s.tprev = dup2(t0);
+		s.botH = dup2(z); s.botF = dup2(z); s.pa = LUT ? 0u : 0x02020202u; s.pb = s.pa;
+		s.Zp = dup2(z);
+		s.thrp = thr_pack(s.thr, b);
 		s.blk = 0x80008000u;
 	}
 
@@ -413,7 +422,7 @@ struct StripS16 {
 					if (lane == 0) { if (!(opt & OPT_NO_SC_FENCE)) __threadfence(); st_release(p.progress + job, flushed); }
 					continue;
 				}
-				start_zero_segment(s, nv_lo, nv_hi);
+				start_zero_segment(s, nv_lo, nv_hi, tmax);
 				computing = true;
 				bm1 = bm2 = INT_MIN;
 			}

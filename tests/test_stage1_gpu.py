@@ -111,6 +111,24 @@ def test_pruning_keeps_best_exact(b200, m, n, hom):
     al.close()
 
 
+def test_pruning_keeps_best_exact_with_million_scores(b200):
+    """Regression (found on the 23M x 25M BASELINE pair): in the lower part of a large, highly similar matrix the
+    surviving band starts at cells worth millions.  A compute segment restarted there with its s16 frame anchored at
+    zero saturated for tmax/32767 blocks, the strips below inherited the under-estimates and the damaged front crept
+    into the alignment path: the pruned run reported a best cell ~5 % short of the exact one.  3M x 3M at 99 % identity
+    reproduces it in seconds; the exact answer is the same kernel with pruning off (itself pinned to the oracle above)."""
+    m = n = 3_000_000
+    a, b = synth.make_pair(m, n, [(0, m)], 0.01, 0.0, 0.0, 0, 41)
+    al = b200.Aligner(kernel=b200.KERNEL_S16X2)
+    al.set_sequences(a, b)
+    exact = al.align_partition(prune=False, use_callbacks=False)
+    r = al.align_partition(prune=True, use_callbacks=False)
+    assert exact["best"][0] > 2_500_000
+    assert r["best"] == exact["best"]
+    assert r["cells"] < 0.8 * exact["cells"]
+    al.close()
+
+
 def test_mixed_alphabet_matches_byte_compare(b200):
     """Real FASTA files carry N runs and IUPAC codes; the reference compares raw bytes (N == N matches).  Strips whose
     rows hold such bytes take the int32 code path inside the same launch, the others stay on the packed kernel."""
