@@ -33,6 +33,26 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries print there too (NCCL writes its version banner to
+    stdout when NCCL_DEBUG=VERSION is set in the environment), so file descriptor 1 is pointed at stderr for the whole
+    run and the JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def make_workload(n_gpus, scale=1.0):
     import synth
     c = dict(synth.CONFIGS["cfg2"])
@@ -149,7 +169,7 @@ def reference_arm(args):
     if rank != 0:
         return 0
     if ref_binary() is None:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/oracle_cpu_block not built (reference mount absent at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/oracle_cpu_block not built (reference mount absent at build time)"})
         return 0
     cores = max(1, min(os.cpu_count() or 1, 32))
     a, b = make_workload(args.gpus, args.scale)
@@ -175,7 +195,7 @@ def reference_arm(args):
                          "sample": f"oracle/_ref/oracle_cpu_block --stage-1 --fork={cores} on the top-left {side}x{side} of the workload (process wall time)"},
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -200,6 +220,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pruning", action="store_true", help="compute every cell (the reference's --no-block-pruning)")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         return reference_arm(args)
 
@@ -359,7 +380,7 @@ def main():
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": side * side / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "port",
                                 "sample": f"oracle/gotoh_oracle.c scalar port on the top-left {side}x{side}, {dt:.1f}s"}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
