@@ -1,0 +1,68 @@
+"""CPU test (no GPU): the cross-compiled library really carries hand-tuned sm_100a code for the hot kernel.
+
+`cuobjdump -sass` of libb200align.so is inspected with tools/sass_step_count.py: the steady wavefront loop of the
+production kernel must be built from the packed DPX instructions (VIADDMNMX.S16x2 / VIMNMX3.S16x2), must stay inside
+the instruction budget the roofline in profiles/r01_inst_per_cell.json is computed from, and must not spill inside the
+loop.  A compiler or source change that silently adds 10 % to the step shows up here, before any GPU time is spent."""
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "masa-cudalign_b200", "libb200align.so")
+KERNEL = "strip_kernel_s16ILi16ELb1ELb1ELb0"          # <R = 16, SW, TRACK, !MIXED>: stage-1 production instance
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(LIB), reason="needs cuobjdump and the built library")
+
+
+def _loops():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sass_step_count.py"), "--lib", LIB, "--kernel", KERNEL],
+                         capture_output=True, text=True, check=True).stdout
+    loops = []
+    for line in out.splitlines():
+        m = re.match(r"loop \S+: (\d+) step\(s\), (\d+) static, (\d+) on the common path = ([\d.]+)/step = ([\d.]+) instr/cell; classes/step: (.*)", line)
+        if m:
+            classes = dict((k, float(v)) for k, v in (kv.rsplit(" ", 1) for kv in m.group(6).split(", ")))
+            loops.append({"steps": int(m.group(1)), "per_step": float(m.group(4)), "per_cell": float(m.group(5)), "classes": classes, "ops": {}})
+        elif line.startswith("   ") and loops:
+            loops[-1]["ops"] = dict((k, float(v)) for k, v in (kv.rsplit(" ", 1) for kv in line.strip().split(", ")))
+    return loops
+
+
+def test_library_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "-lelf", LIB], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+def test_steady_loop_instruction_budget():
+    loops = [l for l in _loops() if l["steps"] == 4 and l["ops"].get("VIADDMNMX", 0) >= 48.0]   # the check-free loops, unrolled by 4
+    assert loops, "steady wavefront loop not found in the SASS"
+    best = min(loops, key=lambda l: l["per_step"])
+    # 16 row pairs per lane-step: E, x, F on VIADDMNMX.S16x2 (+1 for the F-chain bound), H on VIMNMX3.S16x2
+    assert 48.0 <= best["ops"].get("VIADDMNMX", 0) <= 49.0
+    assert best["ops"].get("VIMNMX3", 0) == 16.0
+    assert best["ops"].get("LDS", 0) <= 17.0                               # 16 LUT reads + lane 0's top-border LDS.128
+    assert best["ops"].get("SHFL", 0) == 3.0
+    assert "LDL" not in best["ops"] and "STL" not in best["ops"], "spill inside the steady loop"
+    with open(os.path.join(ROOT, "profiles", "r01_inst_per_cell.json")) as f:
+        budget = json.load(f)["s16x2"]
+    assert best["per_cell"] <= budget * 1.03, (best["per_cell"], budget)   # the roofline denominator stays honest
+    # the exact-maximum variant (used while the best score is < 128) costs the 8 extra VIMNMX3
+    exact = [l for l in loops if l["ops"].get("VIMNMX3", 0) == 24.0]
+    assert exact and min(l["per_step"] for l in exact) <= 160.0
+
+
+def test_kernel_resources():
+    out = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
+    m = re.search(KERNEL + r"[^\n]*\n\s*REG:(\d+) STACK:(\d+) SHARED:(\d+)", out)
+    assert m, "kernel not found"
+    reg, stack, shared = (int(x) for x in m.groups())
+    assert reg <= 128                       # 16 resident warps per SM (4 CTAs x 4 warps)
+    assert shared <= 48 * 1024 + 1024       # static shared memory limit (+ 1 KB reserved by the driver)
+    assert 4 * shared <= 228 * 1024
