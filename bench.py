@@ -333,7 +333,9 @@ def main():
     f_mhz = clocks["sm_mhz"] or peaks.get("sm_max_mhz", 1965.0)
     # raw rate of the dominant kernel per GPU: cells actually COMPUTED / kernel time (CUDA events on the launch stream)
     kernel_gcups = cells * K / dev_total / 1e9 / args.gpus
-    roofline = {"bound": "int-issue", "unit": "GCUPS", "achieved": kernel_gcups, "traffic": ipc_doc.get("dram_bytes_per_launch")}
+    roofline = {"bound": "int-issue", "unit": "GCUPS", "achieved": kernel_gcups, "traffic": ipc_doc.get("dram_bytes_per_launch"),
+                "traffic_def": ipc_doc.get("dram_def"),
+                "achieved_def": "cells actually computed (block pruning skips the rest) / strip-kernel time from CUDA events on its launch stream, per GPU"}
     if ipc:
         peak = 148 * 4 * 32 * f_mhz * 1e6 / ipc / 1e9
         roofline.update({"peak": peak, "frac": kernel_gcups / peak, "inst_per_cell": ipc,
