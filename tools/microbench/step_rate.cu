@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, MINB) step_rate_kernel(St
 		else s.sel[r] = cl | ((8u | cl) << 4) | ((4u + ch) << 8) | ((12u + ch) << 12);
 	}
 	s.tprev = dup2(-kGapFirst); s.botH = 0; s.botF = 0; s.pa = LUT ? 0u : 0x02020202u; s.pb = s.pa;
-	s.Zp = 0; s.base = 0; s.bs = INT_MIN; s.bi = -1; s.bj = -1; s.thr = 30000; s.pub = INT_MIN; s.thrp = dup2(30000); s.ncand = 0;
+	s.Zp = seed[31] >> 31;   // zero, but not a compile-time constant: a literal 0 makes ptxas materialise it once per row (17 PRMT RZ per step)
+	s.base = 0; s.bs = INT_MIN; s.bi = -1; s.bj = -1; s.thr = 30000; s.pub = INT_MIN; s.thrp = dup2(30000); s.ncand = 0;
 	s.blk = 0x80008000u;
 	const int vo = (K::SH - 1) / R, ro = (K::SH - 1) % R;
 	for (int b = 0; b < blocks32; b++) {
