@@ -438,7 +438,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		for (int k = (p->i0 + a) >> 6; k <= (p->i0 + b - 1) >> 6; k++) if (h->bad0[k]) return false;
 		return true;
 	};
-	bool any_s16 = false, any_s32 = false;
+	bool any_s16 = false;
 	{
 		// the packed kernel may be used for a strip iff the caller allows it and the strip's ROWS are pure A/C/G/T
 		// (non-ACGT COLUMN bytes are exact in the packed kernel: they mismatch every A/C/G/T row)
@@ -468,7 +468,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			j.i0 = p->i0 + r; j.rows = end - r; j.j0 = p->j0; j.cols = n;
 			j.dep = (int)h->hjobs.size() - 1;
 			j.flags = (p->first_col_init == B200_INIT_ZEROES && !left_remote) ? JOB_LEFT_ZERO : 0;
-			if (!s16) { j.flags |= JOB_S32; any_s32 = true; } else any_s16 = true;
+			if (!s16) j.flags |= JOB_S32; else any_s16 = true;
 			j.left_off = r;
 			j.right_off = (p->want_last_column || right_remote) ? r : -1;
 			j.sra_off = sra_off;
@@ -634,11 +634,6 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 
 	// ---- hand the artefacts to the caller in the reference's dispatch format
 	if (have_cb) {
-		auto first_col_cell = [&](int rows_above) {   // first-column cell of the row with `rows_above` rows above it, f = -INF
-			Cell c; c.h = 0; c.x = -kInf;
-			return c;
-		};
-		(void)first_col_cell;
 		// first-column H values for the first cell of each dispatched row
 		int last_first_h = 0;
 		if (p->first_col_init != B200_INIT_ZEROES && !left_remote) {
