@@ -4,11 +4,15 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (CUDA, through the C ABI)
   python bench.py --impl reference [--gpus N] ...              the reference's own CPU path (oracle/_ref)
 
-One "step" = one complete stage-1 pass (best score + end coordinate, exact tie-break) over one synthetic pair.
-N = 1: BASELINE config 2 shape, 5 Mbp x 5 Mbp (SURVEY.md 8d cfg2 generator).  N > 1: weak scaling of the
-reference's own multi-GPU scheme (column slices, chained wavefront): rows grow with N (m = 5M*N, n = 5M), every
-GPU owns n/N columns of all rows, the slice-border column streams to the next GPU through peer memory from
-inside the strip kernel (no collective on the data path).  value = m*n*K / (max over ranks of the timed region).
+One "step" = one complete stage-1 pass with block pruning (best score + end coordinate, exact tie-break) over ONE
+synthetic pair that does not depend on N (strong scaling): by default the BASELINE config-3 pair (23M x 25M,
+Drosophila-chromosome shape, the config the metric is quoted on at 1/2/4/8 GPUs) generated at scale 0.4 = 9.2M x 10M,
+the largest scale at which the driver's 25 steps fit its 870 s per-N limit on one GPU; `--workload cfg3 --scale 1`
+runs the full pair (profiles/r02_cfg3_*.json), `--workload cfg5` the 249M x 228M target.  N = 1 runs the single-GPU
+persistent kernel; N > 1 the block-cyclic chain: column chunks dealt round-robin to the GPUs, slice borders stored
+straight into the next GPU's memory from inside the strip kernel, jobs scheduled by on-device events, running best
+shared by peer atomics (no collective on the data path; NCCL only carries the barrier and the final 12-byte bests).
+value = m*n*K / (max over ranks of the timed region), like the reference counts GCUPS (sw_stage1.cpp:444-448).
 """
 import argparse
 import json
@@ -25,8 +29,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 METRIC = "GCUPS (stage-1 SW, device-timed)"
-BASE_M = 5_000_000
-BASE_N = 5_000_000
+BENCH_WORKLOAD = ("cfg3", 0.4)          # default pair of every arm and every N
 
 
 def log(*a):
@@ -53,17 +56,20 @@ def emit(line):
     out.flush()
 
 
-def make_workload(n_gpus, scale=1.0):
+def resolve_workload(args):
+    name, scale = BENCH_WORKLOAD
+    if args.workload:
+        name, scale = args.workload, 1.0
+    if args.scale is not None:
+        scale = args.scale
+    return name, scale
+
+
+def make_workload(args):
+    """The pair depends on (--workload, --scale) only -- never on the number of GPUs."""
     import synth
-    c = dict(synth.CONFIGS["cfg2"])
-    m = int(c["m"] * scale) * n_gpus
-    n = int(c["n"] * scale)
-    # homologous segments follow the main diagonal of the first 5M x 5M square (cfg2), the extra rows of the
-    # weak-scaling variants are unrelated sequence
-    segs = [(int(a0 * scale), int(a1 * scale)) for a0, a1 in c["segs"]]
-    K = c["K"] if scale == 1.0 else int(c["K"] * scale)
-    a, b = synth.make_pair(m, n, segs, c["p_s"], c["p_d"], c["p_i"], K, c["seed"], int(c.get("shift", 0) * scale))
-    return a, b
+    name, scale = resolve_workload(args)
+    return synth.make_config(name, scale)
 
 
 class ClockSampler:
@@ -128,11 +134,13 @@ def measured_peaks():
 
 def inst_per_cell(kernel_used):
     """SASS thread-instructions per DP cell of the dominant kernel, from the committed ncu summary."""
-    p = os.path.join(ROOT, "profiles", "r01_inst_per_cell.json")
-    if os.path.exists(p):
-        with open(p) as f:
-            d = json.load(f)
-        return d.get("s16x2" if kernel_used == 2 else "s32"), d
+    for name in ("r02_inst_per_cell.json", "r01_inst_per_cell.json"):
+        p = os.path.join(ROOT, "profiles", name)
+        if os.path.exists(p):
+            with open(p) as f:
+                d = json.load(f)
+            d["_file"] = "profiles/" + name
+            return d.get("s16x2" if kernel_used == 2 else "s32"), d
     return None, {}
 
 
@@ -172,7 +180,7 @@ def reference_arm(args):
         emit({"impl": "reference", "unavailable": "oracle/_ref/oracle_cpu_block not built (reference mount absent at build time)"})
         return 0
     cores = max(1, min(os.cpu_count() or 1, 32))
-    a, b = make_workload(args.gpus, args.scale)
+    a, b = make_workload(args)
     m, n = a.size, b.size
     # bounded sample: ~1.2e9 cells per core per step (about 5-8 s at the reference's ~0.2 GCUPS/core)
     side = int(min(m, n, (1.2e9 * cores) ** 0.5))
@@ -188,9 +196,11 @@ def reference_arm(args):
     val = side * side * len(times) / total / 1e9
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": total / len(times) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus, m, n), "sample": f"top-left {side}x{side} cells per step"},
+        "config": {"workload": workload_name(args, m, n), "sample": f"top-left {side}x{side} cells per step, every cell computed "
+                   "(--fork disables block pruning in the reference, libmasa.cpp:1318-1321): compare with the GPU arm's "
+                   "config.gcups_computed_cells, not with its whole-matrix value"},
         "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": cores, "kind": "reference",
                          "sample": f"oracle/_ref/oracle_cpu_block --stage-1 --fork={cores} on the top-left {side}x{side} of the workload (process wall time)"},
         "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -199,11 +209,40 @@ def reference_arm(args):
     return 0
 
 
-def workload_name(n_gpus, m, n):
-    if n_gpus == 1:
-        return f"cfg2: {m}x{n} synthetic bacterial-genome-shaped pair (seed 0xC0DA0002), SW stage-1 best score + end coordinate"
-    return (f"cfg2 weak-scaled: {m}x{n} ({n_gpus} x 5M rows, 5M columns split into {n_gpus} column slices, chained wavefront), "
-            "SW stage-1 best score + end coordinate")
+def workload_name(args, m, n):
+    name, scale = resolve_workload(args)
+    shape = {"cfg1": "1M x 1M pair", "cfg2": "bacterial-genome-shaped 5M x 5M pair", "cfg3": "Drosophila-chromosome-shaped 23M x 25M pair",
+             "cfg4": "chr21-shaped 48M x 46M pair", "cfg5": "chr1-shaped 249M x 228M pair"}[name]
+    sc = "" if scale == 1.0 else f" generated at scale {scale}"
+    return (f"{name}: BASELINE {shape}{sc} = {m}x{n} (tools/synth.py, the same pair at every GPU count), "
+            "SW stage-1 with block pruning: best score + end coordinate")
+
+
+def full_alignment_leg(td):
+    """Second half of the BASELINE metric: wall time of a complete alignment (stages 1-6) of the config-2 pair (5M x 5M)
+    through build/cudalign, the drop-in binary (host/B200Aligner behind MASA-Core's own CLI).  N = 1 only."""
+    import synth
+    exe = os.path.join(ROOT, "build", "cudalign")
+    if not os.path.exists(exe):
+        return {"unavailable": "build/cudalign not built (needs the reference headers at build time)"}
+    a, b = synth.make_config("cfg2")
+    fa, fb = os.path.join(td, "cfg2_A.fa"), os.path.join(td, "cfg2_B.fa")
+    synth.write_fasta(fa, a, "synth_cfg2_A"); synth.write_fasta(fb, b, "synth_cfg2_B")
+    wd = os.path.join(td, "w")
+    t0 = time.perf_counter()
+    p = subprocess.run([exe, f"--work-dir={wd}", "--clear", "--verbose=0", "--ram-size=8G", fa, fb], cwd=td,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    dt = time.perf_counter() - t0
+    out = {"workload": "cfg2: 5M x 5M synthetic pair, SW stages 1-6, build/cudalign --ram-size=8G (process start -> alignment.00.txt closed)",
+           "wall_s": dt, "rc": p.returncode}
+    xp = os.path.join(wd, "crosspoints", "crosspoint_01.00")
+    if os.path.exists(xp):
+        out["stage1_crosspoint"] = open(xp).read().split("\n")[1]
+    txt = os.path.join(wd, "alignment.00.txt")
+    out["alignment_txt_bytes"] = os.path.getsize(txt) if os.path.exists(txt) else 0
+    if p.returncode != 0:
+        out["tail"] = p.stdout[-400:]
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -212,12 +251,17 @@ def workload_name(n_gpus, m, n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the workload (development only; the default 1.0 is the benchmark)")
+    ap.add_argument("--workload", default=None, choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"],
+                    help="BASELINE pair to run instead of the default bench pair (cfg3 at scale 0.4)")
+    ap.add_argument("--scale", type=float, default=None, help="scale of the generated pair (default: 0.4 for the bench pair, 1.0 with --workload)")
     ap.add_argument("--kernel", default="auto", choices=["auto", "s32", "s16x2"])
+    ap.add_argument("--chunk-cols", type=int, default=0, help="N > 1: column chunk width (0 = automatic, < 0 = one contiguous slice per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-alignment", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="records of the very large pairs: skip the end-to-end leg")
     ap.add_argument("--no-pruning", action="store_true", help="compute every cell (the reference's --no-block-pruning)")
     args = ap.parse_args()
     protect_stdout()
@@ -245,13 +289,12 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    a, b = make_workload(args.gpus, args.scale)
+    a, b = make_workload(args)
     m, n = a.size, b.size
     kern = {"auto": b200.KERNEL_AUTO, "s32": b200.KERNEL_S32, "s16x2": b200.KERNEL_S16X2}[args.kernel]
     al = b200.Aligner(device=local, kernel=kern)
-    j0, j1 = b200.column_slice(n, rank, world)                     # column slice of this rank (libmasa.cpp:632-635)
     if world > 1:
-        al.mgpu_setup(dist, rank, world, m)
+        al.mgpu_setup(dist, rank, world, m, n, args.chunk_cols)
     al.set_sequences(a, b)                                         # sequences resident in HBM for the `value` leg
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
@@ -262,7 +305,7 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    prune = not args.no_pruning
+    prune = not args.no_pruning and args.kernel != "s32"
 
     def one_step(e2e):
         if e2e:
@@ -270,9 +313,9 @@ def main():
         # block pruning on, as in the reference's stage 1 (C/stage1/sw_stage1.cpp:219-225); GCUPS counts the whole
         # matrix like the reference does (sw_stage1.cpp:444-448), the cells actually computed are reported too
         if world > 1:
-            return al.align_partition(0, j0, m, j1, want_best_score=True, use_callbacks=False, mgpu=True, prune=prune,
-                                      super_i1=m, super_j1=n)
-        return al.align_partition(0, j0, m, j1, want_best_score=True, use_callbacks=False, prune=prune)
+            return al.align_partition(0, 0, m, n, want_best_score=True, use_callbacks=False, mgpu=True, prune=prune,
+                                      chunk_cols=args.chunk_cols)
+        return al.align_partition(0, 0, m, n, want_best_score=True, use_callbacks=False, prune=prune)
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -294,31 +337,31 @@ def main():
     launches = al.kernel_launches() - launches0
     # e2e leg: same metric through the public C ABI with HOST buffers (sequence upload + result read-back timed)
     e2e_times = []
-    for _ in range(max(1, min(args.steps, 2))):
+    for _ in range(0 if args.no_e2e else max(2, min(args.steps, (args.steps + 3) // 4))):
         flush.zero_()
         barrier()
         t0 = time.perf_counter()
         res_e = one_step(True)
         barrier()
         e2e_times.append(time.perf_counter() - t0)
+        if tuple(res_e["best"]) != tuple(res["best"]):
+            log("bench.py: the end-to-end step returned a different best cell"); return 3
     sampler.stop()
 
     total = sum(step_times)
     e2e_total = sum(e2e_times)
+    my = dict(best=tuple(res["best"]), cells=int(res["cells"]), device_ms=sum(dev_ms) / max(len(dev_ms), 1))
     if dist is not None:
         t = torch.tensor([total, e2e_total, sum(dev_ms) / 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total, e2e_total, dev_total = (float(x) for x in t.tolist())
-        bests = [None] * world
-        dist.all_gather_object(bests, tuple(res["best"]))
-        best = b200.merge_best(bests)
-        cells_t = torch.tensor([res["cells"]], dtype=torch.int64, device="cuda")
-        dist.all_reduce(cells_t)
-        cells = int(cells_t.item())
+        per = [None] * world
+        dist.all_gather_object(per, my)
     else:
         dev_total = sum(dev_ms) / 1e3
-        best = tuple(res["best"])
-        cells = res["cells"]
+        per = [my]
+    best = b200.merge_best([p["best"] for p in per])
+    cells = sum(p["cells"] for p in per)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -335,11 +378,11 @@ def main():
     kernel_gcups = cells * K / dev_total / 1e9 / args.gpus
     roofline = {"bound": "int-issue", "unit": "GCUPS", "achieved": kernel_gcups, "traffic": ipc_doc.get("dram_bytes_per_launch"),
                 "traffic_def": ipc_doc.get("dram_def"),
-                "achieved_def": "cells actually computed (block pruning skips the rest) / strip-kernel time from CUDA events on its launch stream, per GPU"}
+                "achieved_def": "cells actually computed (block pruning skips the rest) / strip-kernel time from CUDA events on its launch stream, per GPU (max over GPUs of the kernel time)"}
     if ipc:
         peak = 148 * 4 * 32 * f_mhz * 1e6 / ipc / 1e9
         roofline.update({"peak": peak, "frac": kernel_gcups / peak, "inst_per_cell": ipc,
-                         "peak_def": f"148 SMs x 4 schedulers x 32 lanes x {f_mhz:.0f} MHz (median SM clock sampled under load) / {ipc} SASS thread-instr per cell (ncu, profiles/)"})
+                         "peak_def": f"148 SMs x 4 schedulers x 32 lanes x {f_mhz:.0f} MHz (median SM clock sampled under load) / {ipc} SASS thread-instr per cell ({ipc_doc.get('_file')})"})
         alu = ipc_doc.get("alu_slots_per_cell_s16x2" if kernel_used == 2 else "alu_slots_per_cell_s32")
         if alu:
             apeak = 148 * 64 * f_mhz * 1e6 / alu / 1e9
@@ -347,33 +390,42 @@ def main():
                              "alu_pipe_def": f"148 SMs x 64 lanes/clk (measured VIADDMNMX/VIMNMX issue rate, profiles/r01_pipe_rates.txt) / {alu} ALU-pipe slots per cell"})
     # HBM is not the bound: algorithmic border traffic (16 B per column per strip + 1 B of seq1) vs the measured copy peak
     strips = res["strips"]
-    alg_bytes = strips * (j1 - j0) * 17.0
+    alg_bytes = strips * n * 17.0 / args.gpus
     roofline["hbm"] = {"achieved_gbs": alg_bytes * K / dev_total / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "peak_source": peak_src}
 
+    mean_cells = cells / float(args.gpus)
     line = {
         "metric": METRIC, "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": K, "warmup": args.warmup,
-        "ms_per_step": total / K * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": total / K * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int16x2" if kernel_used == 2 else "int32", "data": "synthetic",
-        "config": {"workload": workload_name(args.gpus, m, n), "m": m, "n": n, "recurrence": "SW affine +1/-3/-3/-2",
+        "config": {"workload": workload_name(args, m, n), "m": m, "n": n, "recurrence": "SW affine +1/-3/-3/-2",
                    "l2": "256 MiB flush buffer written between timed iterations", "kernel": "s16x2" if kernel_used == 2 else "s32",
-                   "strips_per_gpu": strips, "best": list(best), "block_pruning": bool(prune), "cells_computed": cells,
-                   "cells_computed_frac": cells / float(m * n),
+                   "strips": strips, "best": list(best), "block_pruning": bool(prune), "cells_computed": cells,
+                   "cells_computed_frac": cells / float(m * n), "gcups_computed_cells": cells * K / total / 1e9,
+                   "multi_gpu": None if world == 1 else {"scheme": "block-cyclic column chunks, P2P border stores + event-driven job queues in the strip kernel",
+                                                          "chunks": res["chunks"], "chunk_cols": res["chunk_cols"]},
+                   "per_gpu": [{"cells_computed": p["cells"], "kernel_ms_per_step": p["device_ms"], "best": list(p["best"])} for p in per],
+                   "per_gpu_cells_max_over_mean": max(p["cells"] for p in per) / mean_cells if mean_cells else None,
                    "published_other_hw": "README: 5Mx5M 48.98 GCUPS on GTX 560 Ti (all stages); 249Mx228M 82,822 GCUPS on 512xV100"},
         "device_ms_per_step": dev_total / K * 1e3,
         "clocks": clocks,
-        "e2e": {"value": m * n * len(e2e_times) / e2e_total / 1e9, "unit": "GCUPS",
-                "h2d_bytes_per_step": int(m + n), "d2h_bytes_per_step": int(strips * 16 + 32)},
         "gpu_launches": int(launches),
         "roofline": roofline,
     }
-    if not args.no_cpu_baseline and ref_binary() is not None:
-        side = int(min(m, n, 50_000 * max(args.scale, 0.02) ** 0.0))
-        side = min(side, 60_000)
+    if e2e_times:
+        line["e2e"] = {"value": m * n * len(e2e_times) / e2e_total / 1e9, "unit": "GCUPS", "steps": len(e2e_times),
+                       "h2d_bytes_per_step": int(m + n) * args.gpus, "d2h_bytes_per_step": int(strips * 16 + 32) * args.gpus}
+    if world == 1 and not args.no_full_alignment:
+        with tempfile.TemporaryDirectory() as td:
+            line["full_alignment"] = full_alignment_leg(td)
+        line["full_alignment_s"] = line["full_alignment"].get("wall_s")
+    if world == 1 and not args.no_cpu_baseline and ref_binary() is not None:
+        side = min(m, n, 60_000)
         with tempfile.TemporaryDirectory() as td:
             dt, c = run_reference_sample(a, b, side, side, 1, td)
         line["cpu_baseline"] = {"value": c / dt / 1e9, "unit": "GCUPS", "cores": 1, "kind": "reference",
                                 "sample": f"oracle/_ref/oracle_cpu_block --stage-1 --no-block-pruning (reference CPUBlockProcessor, 1 core) on the top-left {side}x{side} of the workload, {dt:.1f}s"}
-    elif not args.no_cpu_baseline:
+    elif world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         import oracle_lib as O
         side = min(m, n, 20_000)

@@ -74,7 +74,7 @@ typedef struct {
 	int want_best_score;         /* IManager::mustDispatchScores: exact best cell of the partition */
 	int prune;                   /* IManager::mustPruneBlocks */
 	int super_i1, super_j1;      /* IManager::getSuperPartition: bounds used by the pruning test */
-	int reserved[4];             /* [0] flags: B200_MGPU_CHAIN | B200_CONT_CHUNK; [1] column offset of a chained slice;
+	int reserved[4];             /* [0] flags: B200_MGPU_CHAIN | B200_CONT_CHUNK; [1] chunk width of a chained call;
 	                                [2] rows of the partition already aligned by earlier chunk calls; [3] total rows of
 	                                the partition (0 = i1-i0): the special-row policy is applied to the WHOLE partition */
 } b200_partition;
@@ -106,7 +106,7 @@ typedef struct {
 	int strips;                  /* strip jobs executed */
 	int kernel_launches;         /* kernels launched by this call */
 	int kernel_used;             /* B200_KERNEL_S32 | B200_KERNEL_S16X2 */
-	int reserved[5];
+	int reserved[5];             /* chained calls: [0] column chunks, [1] widest chunk */
 } b200_result;
 
 typedef struct b200_handle b200_handle;
@@ -142,22 +142,57 @@ int b200_diag_end(b200_handle* h);                                              
 int b200_match_last_column(b200_handle* h, const b200_cell* buffer, const b200_cell* base, int len, int goal,
                            b200_match* out);
 
-/* Multi-GPU chained wavefront on one NVLink/NVSwitch box: one process (and one b200_handle) per GPU, seq1 split
- * into contiguous column slices exactly like the reference's --fork/--split (C/libmasa/libmasa.cpp:540-642), but
- * the slice-border column never touches the host or a socket (reference: SocketCellsWriter/Reader + Buffer2,
- * C/stage1/sw_stage1.cpp:168-186): the strip kernel of GPU g stores its right border straight into the
- * exchange block of GPU g+1 (peer memory, P2P stores) and releases a system-scope row counter that the strip
- * warps of g+1 acquire before they load their left border.  The running best score is pushed to every peer
- * (peer atomicMax), replacing AlignerPool's file+signal polling (C/common/AlignerPool.cpp:46-68).
- *   1. every rank: b200_mgpu_export(h, max_rows, &mine)
- *   2. exchange the 64-byte handles out of band (torch.distributed all_gather in bench.py)
+/* Multi-GPU chained wavefront on one NVLink/NVSwitch box.  The reference splits seq1 into one contiguous column
+ * slice per process (--fork/--split, C/libmasa/libmasa.cpp:540-642) and streams the slice border through TCP sockets
+ * (SocketCellsWriter/Reader + Buffer2, C/stage1/sw_stage1.cpp:168-186); block pruning is switched off in that mode
+ * (libmasa.cpp:1318-1321).  Here the columns are cut into CHUNKS dealt round-robin to the GPUs (chunk c belongs to GPU
+ * c mod world): every strip of rows travels GPU 0 -> 1 -> ... -> world-1 -> 0 -> ... once per chunk.  The strip kernel
+ * stores the right border of a (strip, chunk) job straight into the exchange block of the next GPU (peer memory, P2P
+ * stores over NVLink) and then counts a "left event" on that strip's event word over there; the job on the right is
+ * pushed into that GPU's work queue as soon as its left border AND the first columns of the strip above exist, and
+ * resident warps pop jobs from the queue (dataflow scheduling, no host, no socket, no collective on the data path).
+ * Round-robin chunks spread the cells that survive block pruning evenly over the GPUs (the reference's static slices
+ * cannot: README "MultiBP"), and a pipeline hop costs one chunk sweep instead of one slice sweep.  The running best
+ * score is pushed to every peer (peer atomicMax), replacing AlignerPool's file+signal polling
+ * (C/common/AlignerPool.cpp:46-68), so pruning stays ON.
+ *
+ * One process per GPU (bench.py, tests/mgpu_check.py under torchrun):
+ *   1. every rank: b200_chain_plan(partition, world, &info); b200_mgpu_export(h, rows, info.max_jobs, &mine)
+ *   2. exchange the 64-byte handles out of band (torch.distributed all_gather)
  *   3. every rank: b200_mgpu_connect(h, rank, world, all_handles)
- *   4. every rank: b200_align_partition with b200_partition.reserved[0] = B200_MGPU_CHAIN on its own slice */
+ *   4. every rank: b200_align_partition with the WHOLE partition and b200_partition.reserved[0] = B200_MGPU_CHAIN;
+ *      reserved[1] = chunk width in columns (0 = automatic, < 0 = one contiguous slice per GPU with the reference's
+ *      --split arithmetic, libmasa.cpp:632-635).  Each rank gets the artefacts of ITS chunks: dispatch_row delivers
+ *      [first-column cell, rank 0 only] and then one call per owned chunk in column order; dispatch_column / the last
+ *      row's tail come from the owner of the last chunk; b200_result.best is the best cell of the rank's own chunks.
+ *      Consecutive chained calls must be separated by a barrier over all ranks.
+ * One process for all GPUs (build/cudalign --gpus=N): b200_group_* below; same kernels, peers mapped with
+ * cudaDeviceEnablePeerAccess, artefacts delivered exactly like the single-GPU call (whole rows, merged best). */
 typedef struct { unsigned char bytes[64]; } b200_ipc_handle;
+typedef struct {
+	int chunks;                  /* column chunks of the partition */
+	int chunk_cols;              /* width of a chunk (the last one may be narrower) */
+	int chunks_per_gpu;          /* most chunks owned by one GPU */
+	int reserved0;
+	long long max_strips;        /* upper bound of the strips of the partition */
+	long long max_jobs;          /* capacity to pass to b200_mgpu_export / b200_group_create */
+} b200_chain_info;
 #define B200_MGPU_CHAIN 1
-int b200_mgpu_export(b200_handle* h, int max_rows, b200_ipc_handle* out);
+int b200_chain_plan(const b200_partition* p, int world, b200_chain_info* out);      /* host only, no GPU needed */
+int b200_mgpu_export(b200_handle* h, long long max_rows, long long max_jobs, b200_ipc_handle* out);
 int b200_mgpu_connect(b200_handle* h, int rank, int world, const b200_ipc_handle* all_handles);
 int b200_mgpu_disconnect(b200_handle* h);
+int b200_last_chain_result(const b200_handle* h, b200_result* out);   /* this GPU's share of the last chained call */
+
+typedef struct b200_group b200_group;
+int b200_group_create(const int* devices, int n, const b200_config* cfg, long long max_rows, long long max_jobs, b200_group** out);
+void b200_group_destroy(b200_group* g);
+const char* b200_group_last_error(const b200_group* g);
+int b200_group_size(const b200_group* g);
+b200_handle* b200_group_handle(b200_group* g, int rank);            /* rank 0 serves the single-GPU calls (stages 2-4) */
+int b200_group_set_sequences(b200_group* g, const char* seq0, int seq0_len, const char* seq1, int seq1_len);
+int b200_group_align_partition(b200_group* g, const b200_partition* p, const b200_callbacks* cb, b200_result* out);
+int b200_group_rank_result(const b200_group* g, int rank, b200_result* out);        /* cells / device time per GPU */
 
 /* Stage 4: batched Myers-Miller partition split on the GPU (replaces reduce_partitions/split_thread/ort_split_2 of
  * C/stage4/sw_stage4.cpp:87-380,806-852, 4 pthreads in the reference).  Crosspoints are the reference's

@@ -46,6 +46,11 @@ class Result(C.Structure):
                 ("strips", C.c_int), ("kernel_launches", C.c_int), ("kernel_used", C.c_int), ("reserved", C.c_int * 5)]
 
 
+class ChainInfo(C.Structure):
+    _fields_ = [("chunks", C.c_int), ("chunk_cols", C.c_int), ("chunks_per_gpu", C.c_int), ("reserved0", C.c_int),
+                ("max_strips", C.c_longlong), ("max_jobs", C.c_longlong)]
+
+
 RECV_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)
 DISP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_int)
 SCORE_FN = C.CFUNCTYPE(None, C.c_void_p, Score)
@@ -63,7 +68,10 @@ EXPORTS = [
     "b200_unset_sequences", "b200_align_partition", "b200_diag_begin", "b200_diag_set_first_row",
     "b200_diag_set_first_column", "b200_diag_process", "b200_diag_get_row", "b200_diag_get_last_column",
     "b200_diag_get_block_scores", "b200_diag_clear_pruned", "b200_diag_end", "b200_match_last_column",
-    "b200_processed_cells", "b200_kernel_launches", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect", "b200_special_row_ids", "b200_stage4_round", "b200_stage4",
+    "b200_processed_cells", "b200_kernel_launches", "b200_chain_plan", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect",
+    "b200_last_chain_result", "b200_group_create", "b200_group_destroy", "b200_group_last_error", "b200_group_size", "b200_group_handle",
+    "b200_group_set_sequences", "b200_group_align_partition", "b200_group_rank_result",
+    "b200_special_row_ids", "b200_stage4_round", "b200_stage4",
 ]
 
 _lib = None
@@ -97,7 +105,20 @@ def load_library(path=None):
     lib.b200_processed_cells.restype = C.c_longlong
     lib.b200_kernel_launches.argtypes = [C.c_void_p]
     lib.b200_kernel_launches.restype = C.c_longlong
-    lib.b200_mgpu_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.b200_chain_plan.argtypes = [C.POINTER(Partition), C.c_int, C.POINTER(ChainInfo)]
+    lib.b200_mgpu_export.argtypes = [C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p]
+    lib.b200_last_chain_result.argtypes = [C.c_void_p, C.POINTER(Result)]
+    lib.b200_group_create.argtypes = [C.c_void_p, C.c_int, C.POINTER(Config), C.c_longlong, C.c_longlong, C.POINTER(C.c_void_p)]
+    lib.b200_group_destroy.argtypes = [C.c_void_p]
+    lib.b200_group_destroy.restype = None
+    lib.b200_group_last_error.argtypes = [C.c_void_p]
+    lib.b200_group_last_error.restype = C.c_char_p
+    lib.b200_group_size.argtypes = [C.c_void_p]
+    lib.b200_group_handle.argtypes = [C.c_void_p, C.c_int]
+    lib.b200_group_handle.restype = C.c_void_p
+    lib.b200_group_set_sequences.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    lib.b200_group_align_partition.argtypes = [C.c_void_p, C.POINTER(Partition), C.POINTER(Callbacks), C.POINTER(Result)]
+    lib.b200_group_rank_result.argtypes = [C.c_void_p, C.c_int, C.POINTER(Result)]
     lib.b200_mgpu_connect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.b200_mgpu_disconnect.argtypes = [C.c_void_p]
     lib.b200_special_row_ids.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
@@ -118,9 +139,31 @@ def special_row_ids(height, block_height, interval):
 
 
 def column_slice(n, rank, world):
-    """Columns [j0, j1) owned by `rank` in the chained multi-GPU wavefront: equal weights, the integer arithmetic of
-    the reference's --split/--fork (C/libmasa/libmasa.cpp:632-635)."""
+    """Columns [j0, j1) of `rank` when the chain runs with one contiguous slice per GPU (chunk_cols < 0): equal
+    weights, the integer arithmetic of the reference's --split/--fork (C/libmasa/libmasa.cpp:632-635)."""
     return n * rank // world, n * (rank + 1) // world
+
+
+def chain_plan(m, n, world, chunk_cols=0):
+    """Column chunks of a chained m x n partition (host-side planning, no GPU): dict(chunks, chunk_cols,
+    chunks_per_gpu, max_strips, max_jobs).  Chunk c = columns [c * chunk_cols, ...) belongs to GPU c % world."""
+    lib = load_library()
+    part = Partition(i0=0, j0=0, i1=m, j1=n)
+    part.reserved[1] = chunk_cols
+    info = ChainInfo()
+    if lib.b200_chain_plan(C.byref(part), world, C.byref(info)) != 0:
+        raise B200Error("b200_chain_plan: bad arguments")
+    return {k: getattr(info, k) for k in ("chunks", "chunk_cols", "chunks_per_gpu", "max_strips", "max_jobs")}
+
+
+def chain_chunks(n, world, chunk_cols=0):
+    """[(j0, j1, owner)] of every chunk of an n-column chained partition."""
+    if chunk_cols < 0:
+        b = sorted(set(n * r // world for r in range(world + 1)))
+    else:
+        w = chain_plan(1, n, world, chunk_cols)["chunk_cols"]
+        b = list(range(0, n, w)) + [n]
+    return [(b[c], b[c + 1], c % world) for c in range(len(b) - 1)]
 
 
 def merge_best(bests):
@@ -177,7 +220,8 @@ class Aligner:
     def align_partition(self, i0=0, j0=0, i1=None, j1=None, recurrence=SMITH_WATERMAN, first_row_init=INIT_ZEROES,
                         first_col_init=INIT_ZEROES, first_row=None, first_col=None, special_row_interval=0,
                         block_height=0, want_special_rows=False, want_last_row=False, want_last_column=False,
-                        want_best_score=True, prune=False, use_callbacks=True, mgpu=False, super_i1=None, super_j1=None):
+                        want_best_score=True, prune=False, use_callbacks=True, mgpu=False, super_i1=None, super_j1=None,
+                        chunk_cols=0, group=None):
         """Run b200_align_partition.  first_row / first_col: CELL arrays INCLUDING the corner as element 0
         (n+1 / m+1 cells), used when the init type is INIT_CUSTOM (or to feed gaps through the callback path)."""
         a, b = self._seqs
@@ -190,7 +234,8 @@ class Aligner:
                          want_best_score=int(want_best_score), prune=int(prune), super_i1=i1 if super_i1 is None else super_i1,
                          super_j1=j1 if super_j1 is None else super_j1)
         if mgpu:
-            part.reserved[0] = 1          # B200_MGPU_CHAIN
+            part.reserved[0] = 1          # B200_MGPU_CHAIN: the partition is the WHOLE one, this rank aligns its chunks
+            part.reserved[1] = chunk_cols
         out = {"rows": {}, "row_first": {}, "last_column": [], "scores": []}
         pos = {"row": 0, "col": 0}
 
@@ -229,8 +274,14 @@ class Aligner:
                     SCORE_FN(disp_score), CONT_FN(lambda _c: 1)]
             cbs = Callbacks(None, *keep)
         res = Result()
-        rc = self.lib.b200_align_partition(self.h, C.byref(part), C.byref(cbs) if cbs is not None else None, C.byref(res))
-        self._check(rc, "b200_align_partition")
+        if group is not None:
+            part.reserved[1] = chunk_cols
+            rc = self.lib.b200_group_align_partition(group, C.byref(part), C.byref(cbs) if cbs is not None else None, C.byref(res))
+            if rc != 0:
+                raise B200Error("b200_group_align_partition failed: " + self.lib.b200_group_last_error(group).decode())
+        else:
+            rc = self.lib.b200_align_partition(self.h, C.byref(part), C.byref(cbs) if cbs is not None else None, C.byref(res))
+            self._check(rc, "b200_align_partition")
         out["best"] = (res.best.score, res.best.i, res.best.j)
         out["cells"] = res.cells
         out["cells_total"] = res.cells_total
@@ -238,19 +289,31 @@ class Aligner:
         out["strips"] = res.strips
         out["kernel_launches"] = res.kernel_launches
         out["kernel_used"] = res.kernel_used
+        out["chunks"] = res.reserved[0]
+        out["chunk_cols"] = res.reserved[1]
         out["rows"] = {i: np.concatenate(v) for i, v in out["rows"].items()}
         out["last_column"] = np.concatenate(out["last_column"]) if out["last_column"] else np.zeros(0, CELL)
         return out
 
     # ---- multi-GPU chain -----------------------------------------------------------------------------
-    def mgpu_setup(self, dist, rank, world, max_rows):
-        """Export this rank's exchange block, all-gather the IPC handles over torch.distributed, map the peers."""
+    def mgpu_setup(self, dist, rank, world, max_rows, max_cols, chunk_cols=0):
+        """Export this rank's exchange block (sized for chained partitions of up to max_rows x max_cols with the given
+        chunk width), all-gather the IPC handles over torch.distributed (dist=None: world 1, the GPU is its own
+        neighbour), map the peers."""
+        plan = chain_plan(max_rows, max_cols, world, chunk_cols)
         mine = (C.c_ubyte * 64)()
-        self._check(self.lib.b200_mgpu_export(self.h, max_rows, mine), "b200_mgpu_export")
-        handles = [None] * world
-        dist.all_gather_object(handles, bytes(mine))
+        self._check(self.lib.b200_mgpu_export(self.h, max_rows, plan["max_jobs"], mine), "b200_mgpu_export")
+        handles = [bytes(mine)]
+        if dist is not None:
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(mine))
         blob = (C.c_ubyte * (64 * world)).from_buffer_copy(b"".join(handles))
         self._check(self.lib.b200_mgpu_connect(self.h, rank, world, blob), "b200_mgpu_connect")
+
+    def last_chain_result(self):
+        r = Result()
+        self._check(self.lib.b200_last_chain_result(self.h, C.byref(r)), "b200_last_chain_result")
+        return dict(best=(r.best.score, r.best.i, r.best.j), cells=r.cells, cells_total=r.cells_total, device_ms=r.device_ms)
 
     # ---- diag primitives -------------------------------------------------------------------------------
     def diag_begin(self, part: Partition, split, block_height):
@@ -318,3 +381,47 @@ class Aligner:
 
     def kernel_launches(self):
         return self.lib.b200_kernel_launches(self.h)
+
+
+class Group:
+    """Several GPUs driven by one process (b200_group_*): the multi-GPU mode of build/cudalign.  align_partition()
+    has the semantics of the single-GPU call (whole rows, whole last column, merged best)."""
+
+    def __init__(self, devices, max_rows, max_cols, chunk_cols=0, kernel=KERNEL_AUTO):
+        self.lib = load_library()
+        self.devices = list(devices)
+        plan = chain_plan(max_rows, max_cols, len(self.devices), chunk_cols)
+        dev = (C.c_int * len(self.devices))(*self.devices)
+        cfg = Config(device=0, kernel=kernel, warps_per_sm=0)
+        self.g = C.c_void_p()
+        rc = self.lib.b200_group_create(dev, len(self.devices), C.byref(cfg), max_rows, plan["max_jobs"], C.byref(self.g))
+        if rc != 0:
+            raise B200Error("b200_group_create failed: " + self.lib.b200_group_last_error(None).decode())
+        # a non-owning Aligner view of rank 0 reuses the callback plumbing of Aligner.align_partition
+        self._view = Aligner.__new__(Aligner)
+        self._view.lib = self.lib
+        self._view.h = C.c_void_p()            # not owned: never destroyed through the view
+        self._view._seqs = None
+
+    def close(self):
+        if self.g:
+            self.lib.b200_group_destroy(self.g)
+            self.g = C.c_void_p()
+
+    def set_sequences(self, s0, s1):
+        a, b = _as_u8(s0), _as_u8(s1)
+        self._view._seqs = (a, b)
+        rc = self.lib.b200_group_set_sequences(self.g, a.ctypes.data, a.size, b.ctypes.data, b.size)
+        if rc != 0:
+            raise B200Error("b200_group_set_sequences failed: " + self.lib.b200_group_last_error(self.g).decode())
+
+    def align_partition(self, **kw):
+        return self._view.align_partition(group=self.g, **kw)
+
+    def rank_results(self):
+        out = []
+        for r in range(len(self.devices)):
+            res = Result()
+            self.lib.b200_group_rank_result(self.g, r, C.byref(res))
+            out.append(dict(best=(res.best.score, res.best.i, res.best.j), cells=res.cells, cells_total=res.cells_total, device_ms=res.device_ms))
+        return out

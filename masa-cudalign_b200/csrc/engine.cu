@@ -78,6 +78,9 @@ struct b200_handle {
 	DevBuf<int> progress;
 	DevBuf<Score3> results;
 	DevBuf<int> scalars;            // [0] job counter, [1] global best, [2] stop flag, [4..5] cells (u64)
+	DevBuf<Cell> matchbuf;          // scratch of b200_match_last_column (its own: the call may come between chunked launches)
+	DevBuf<int> matchflag;
+	PinBuf<int> hmatchflag;
 	PinBuf<Cell> hcells;            // pinned staging for rows / columns
 	PinBuf<Score3> hresults;
 	PinBuf<int> hscalars;
@@ -98,23 +101,30 @@ struct b200_handle {
 		PinBuf<Cell> hlastcol; int hlastcol_diag = -2;
 	} dg;
 
-	// multi-GPU chain: exchange block = [64 control ints][max_rows+1 cells]; ctrl[0] = rows of our left border
-	// delivered by the previous GPU, ctrl[1] = running best shared by all GPUs
+	// multi-GPU chain: one peer-visible exchange block per GPU (ExLayout below): control words (running best, queue tail),
+	// per-strip event words, the work queue, and the left-border cells delivered by the GPU on our left
 	struct {
 		int* block = nullptr;
-		size_t max_rows = 0;
+		long long cap_rows = 0, cap_strips = 0, cap_jobs = 0;
 		int rank = -1, world = 0;
 		int* peers[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 		bool connected = false;
+		bool ipc = false;              // peers were mapped with cudaIpcOpenMemHandle (one process per GPU) rather than peer access
+		unsigned epoch = 0;            // chained calls made so far: selects the running-best word
+		DevBuf<StripRow> strips;
+		DevBuf<ChunkCol> chunks;
+		PinBuf<Cell> hrow;             // pinned staging for rows assembled from several GPUs
 	} mg;
+	b200_result last_chain;            // per-GPU figures of the last chained call (b200_group_rank_result)
 	// per-launch overrides of the border / sharing pointers (diag mode and chain mode)
 	struct {
-		const Cell* left = nullptr; Cell* right = nullptr;
-		const int* left_ready = nullptr; int* right_ready = nullptr;
+		const Cell* left = nullptr; Cell* right = nullptr; bool no_right = false;
+		ChainParams chain;
 		int* gbest = nullptr; int* peer_best[8]; int npeer = 0;
 		int prune = 0, prune_i1 = 0, prune_j1 = 0;
 		const unsigned char* s0 = nullptr; const unsigned char* s1 = nullptr; Cell* busH = nullptr;
 		int job_off = 0; int* counter = nullptr;
+		long long chunk_cols_max = 0;
 		int* sra_done = nullptr;
 		bool mixed = false;
 	} ov;
@@ -194,6 +204,17 @@ int strip_opt() {
 	return e ? atoi(e) : kDefaultStripOpt;
 }
 
+// Time without observable progress after which a spin-wait gives up (strip_common.cuh Watchdog).  A wait in the chain
+// is legitimately as long as the sweep of one column chunk on every other GPU; B200_WATCHDOG_S overrides (0 = never).
+long long watchdog_ns(b200_handle* h) {
+	const char* e = getenv("B200_WATCHDOG_S");
+	if (e) return (long long)(atof(e) * 1e9);
+	long long ns = 30LL * 1000000000LL;
+	if (h->ov.chain.enabled)      // 2 us per column and hop: four times the sweep time of a chunk at full occupancy
+		ns += h->ov.chunk_cols_max * 2000LL * std::max(1, h->ov.chain.world);
+	return ns;
+}
+
 int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 	int per_sm = 0;
 	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kWarpsPerBlock * 32, 0);
@@ -202,7 +223,7 @@ int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 	if (h->cfg.warps_per_sm > 0) lim = std::min(lim, h->cfg.warps_per_sm);
 	int best_w = lim;
 	// with pruning about half of the resident strips are skipping (and mostly sleeping): keep every slot occupied
-	if (h->cfg.warps_per_sm <= 0 && chained && !h->ov.prune && njobs > h->sm_count * kSatWarps) {
+	if (h->cfg.warps_per_sm <= 0 && chained && !h->ov.prune && !h->ov.chain.enabled && njobs > h->sm_count * kSatWarps) {
 		double best_cost = 1e300;
 		for (int w = std::min(kSatWarps, lim); w <= lim; w++) {
 			long long cap = (long long)h->sm_count * w;
@@ -222,8 +243,10 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.s0 = h->ov.s0 ? h->ov.s0 : h->s0.p; sp.s1 = h->ov.s1 ? h->ov.s1 : h->s1.p;
 	sp.busH = h->ov.busH ? h->ov.busH : h->busH.p; sp.sra = h->sra.p;
 	sp.left = h->ov.left ? h->ov.left : h->left.p;
-	sp.right = h->ov.right ? h->ov.right : h->right.p;
-	sp.left_ready = h->ov.left_ready; sp.right_ready = h->ov.right_ready;
+	sp.right = h->ov.no_right ? nullptr : (h->ov.right ? h->ov.right : h->right.p);
+	sp.chain = h->ov.chain;
+	sp.watchdog_ns = watchdog_ns(h);
+	{ const char* e = getenv("B200_TEST_DELAY_MS"); sp.test_delay_ms = e ? atoi(e) : 0; }
 	sp.n_peer_best = h->ov.npeer;
 	for (int k = 0; k < 8; k++) sp.peer_best[k] = k < h->ov.npeer ? h->ov.peer_best[k] : nullptr;
 	sp.jobs = h->jobs.p + h->ov.job_off; sp.njobs = njobs;
@@ -302,6 +325,8 @@ extern "C" int b200_create(const b200_config* cfg, b200_handle** out) {
 	}
 	b200_handle* h = new b200_handle();
 	memset(&h->cfg, 0, sizeof(h->cfg));
+	memset(&h->ov.chain, 0, sizeof(h->ov.chain));
+	memset(&h->last_chain, 0, sizeof(h->last_chain));
 	if (cfg) h->cfg = *cfg;
 	h->cont_corner.h = 0; h->cont_corner.x = -kInf;
 	if (h->cfg.device < 0 || h->cfg.device >= ndev) h->cfg.device = h->cfg.device < 0 ? 0 : h->cfg.device % ndev;   // wrap like R/src/CUDAligner.cpp:142-148
@@ -330,6 +355,7 @@ extern "C" void b200_destroy(b200_handle* h) {
 	h->s0.release(); h->s1.release(); h->busH.release(); h->left.release(); h->right.release(); h->sra.release();
 	h->jobs.release(); h->progress.release(); h->results.release(); h->scalars.release();
 	h->hcells.release(); h->hresults.release(); h->hscalars.release();
+	h->matchbuf.release(); h->matchflag.release(); h->hmatchflag.release();
 	h->dg.vbuf.release(); h->dg.col0.release(); h->dg.hlastcol.release();
 	h->s4.s0r.release(); h->s4.s1r.release(); h->s4.left.release(); h->s4.halves.release(); h->s4.parts.release(); h->s4.out.release();
 	for (int k = 0; k < 4; k++) h->s4.bus[k].release();
@@ -404,9 +430,54 @@ extern "C" int b200_special_row_ids(int height, int block_height, int interval, 
 	return (int)ids.size();
 }
 
+// Strips of a partition: cut every kSH16F (packed) / kSH32 (int32) rows and additionally at the reference's special-row
+// ids, so that every special row is the bottom row of a strip.  Identical on every GPU of a chain.
+static void build_strips(b200_handle* h, const b200_partition* p, int m, const std::vector<int>& sr_ids,
+                         std::vector<StripRow>& rows, bool& any_s16) {
+	rows.clear();
+	any_s16 = false;
+	// rows [a, b) of the partition free of non-ACGT bytes?  (64-row granularity, conservative)
+	auto rows_clean = [&](int a, int b) {
+		if (h->acgt_only) return true;
+		for (int k = (p->i0 + a) >> 6; k <= (p->i0 + b - 1) >> 6; k++) if (h->bad0[k]) return false;
+		return true;
+	};
+	// the packed kernel may be used for a strip iff the caller allows it and the strip's ROWS are pure A/C/G/T
+	// (non-ACGT COLUMN bytes are exact in the packed kernel: they mismatch every A/C/G/T row)
+	const bool allow16 = (h->cfg.kernel == B200_KERNEL_AUTO || h->cfg.kernel == B200_KERNEL_S16X2);
+	size_t next_sr = 0;
+	int r = 0;
+	while (r < m) {
+		int lim = m;
+		if (next_sr < sr_ids.size()) lim = std::min(lim, sr_ids[next_sr]);
+		int end;
+		bool s16;
+		if (allow16 && rows_clean(r, std::min(lim, r + kSH32))) {
+			s16 = true;
+			end = std::min(lim, r + kSH32);
+			if (end == r + kSH32 && end < lim && rows_clean(end, std::min(lim, r + kSH16F))) end = std::min(lim, r + kSH16F);
+		} else {
+			s16 = false;
+			end = std::min(lim, r + kSH32);
+		}
+		StripRow sr;
+		memset(&sr, 0, sizeof(sr));
+		sr.i0 = p->i0 + r; sr.rows = end - r; sr.left_off = r;
+		sr.flags = s16 ? 0 : JOB_S32;
+		sr.sra_row = -1;
+		if (next_sr < sr_ids.size() && sr_ids[next_sr] == end) sr.sra_row = (int)next_sr++;
+		if (s16) any_s16 = true;
+		rows.push_back(sr);
+		r = end;
+	}
+}
+
+static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition* p, const b200_callbacks* cb, b200_result* out);
+
 extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, const b200_callbacks* cb, b200_result* out) {
 	if (!h) return 1;
 	if (!p || !out) { h->err = "b200_align_partition: bad arguments"; return 1; }
+	if (p->reserved[0] & B200_MGPU_CHAIN) return chain_align(&h, 1, p, cb, out);
 	memset(out, 0, sizeof(*out));
 	const int m = p->i1 - p->i0, n = p->j1 - p->j0;
 	if (m <= 0 || n <= 0 || p->i0 < 0 || p->j0 < 0 || p->i1 > h->n0 || p->j1 > h->n1) { h->err = "b200_align_partition: partition outside the sequences"; return 1; }
@@ -415,13 +486,9 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	const int SH = kSH16F;
 	const bool sw = p->recurrence == B200_SMITH_WATERMAN;
 	const int track = p->want_best_score ? 2 : 0;
-	const bool chain = (p->reserved[0] & B200_MGPU_CHAIN) != 0;
 	const bool cont = (p->reserved[0] & B200_CONT_CHUNK) != 0;
 	const int row_offset = p->reserved[2];
 	const int total_rows = p->reserved[3] > 0 ? p->reserved[3] : m;
-	if (chain && (!h->mg.connected || (size_t)m > h->mg.max_rows)) { h->err = "b200_align_partition: multi-GPU chain requested but b200_mgpu_connect was not called (or max_rows too small)"; return 1; }
-	const bool left_remote = chain && h->mg.rank > 0;
-	const bool right_remote = chain && h->mg.rank + 1 < h->mg.world;
 
 	// ---- special rows and strips
 	int bh = p->block_height > 0 ? p->block_height : 4 * std::min(128, n);
@@ -431,51 +498,21 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		special_row_ids(total_rows, bh, p->special_row_interval, all_ids);
 		for (int g : all_ids) if (g > row_offset && g <= row_offset + m) sr_ids.push_back(g - row_offset);
 	}
-	h->hjobs.clear();
-	// rows [a, b) of the partition free of non-ACGT bytes?  (64-row granularity, conservative)
-	auto rows_clean = [&](int a, int b) {
-		if (h->acgt_only) return true;
-		for (int k = (p->i0 + a) >> 6; k <= (p->i0 + b - 1) >> 6; k++) if (h->bad0[k]) return false;
-		return true;
-	};
+	std::vector<StripRow> srows;
 	bool any_s16 = false;
-	{
-		// the packed kernel may be used for a strip iff the caller allows it and the strip's ROWS are pure A/C/G/T
-		// (non-ACGT COLUMN bytes are exact in the packed kernel: they mismatch every A/C/G/T row)
-		const bool allow16 = (h->cfg.kernel == B200_KERNEL_AUTO || h->cfg.kernel == B200_KERNEL_S16X2);
-		size_t next_sr = 0;
-		int r = 0;
-		while (r < m) {
-			int lim = m;
-			if (next_sr < sr_ids.size()) lim = std::min(lim, sr_ids[next_sr]);
-			int end;
-			bool s16;
-			if (allow16 && rows_clean(r, std::min(lim, r + kSH32))) {
-				s16 = true;
-				end = std::min(lim, r + kSH32);
-				if (end == r + kSH32 && end < lim && rows_clean(end, std::min(lim, r + kSH16F))) end = std::min(lim, r + kSH16F);
-			} else {
-				s16 = false;
-				end = std::min(lim, r + kSH32);
-			}
-			long long sra_off = -1;
-			if (next_sr < sr_ids.size() && sr_ids[next_sr] == end) {
-				sra_off = (long long)next_sr * n;
-				next_sr++;
-			}
-			StripJob j;
-			memset(&j, 0, sizeof(j));
-			j.i0 = p->i0 + r; j.rows = end - r; j.j0 = p->j0; j.cols = n;
-			j.dep = (int)h->hjobs.size() - 1;
-			j.flags = (p->first_col_init == B200_INIT_ZEROES && !left_remote) ? JOB_LEFT_ZERO : 0;
-			if (!s16) j.flags |= JOB_S32; else any_s16 = true;
-			j.left_off = r;
-			j.right_off = (p->want_last_column || right_remote) ? r : -1;
-			j.sra_off = sra_off;
-			j.sra_index = sra_off >= 0 ? sra_off / n : -1;
-			h->hjobs.push_back(j);
-			r = end;
-		}
+	build_strips(h, p, m, sr_ids, srows, any_s16);
+	h->hjobs.clear();
+	for (const StripRow& sr : srows) {
+		StripJob j;
+		memset(&j, 0, sizeof(j));
+		j.i0 = sr.i0; j.rows = sr.rows; j.j0 = p->j0; j.cols = n;
+		j.dep = (int)h->hjobs.size() - 1;
+		j.flags = sr.flags | (p->first_col_init == B200_INIT_ZEROES ? JOB_LEFT_ZERO : 0);
+		j.left_off = sr.left_off;
+		j.right_off = p->want_last_column ? sr.left_off : -1;
+		j.sra_off = sr.sra_row >= 0 ? (long long)sr.sra_row * n : -1;
+		j.sra_index = sr.sra_row;
+		h->hjobs.push_back(j);
 	}
 	const int njobs = (int)h->hjobs.size();
 	if (!any_s16) kind = B200_KERNEL_S32;
@@ -487,8 +524,12 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	CU(h, h->hresults.reserve(njobs));
 	if (!sr_ids.empty()) CU(h, h->sra.reserve(sr_ids.size() * (size_t)n));
 	if (p->want_last_column) CU(h, h->right.reserve((size_t)m + 1));
-	size_t stage_cells = std::max<size_t>((size_t)std::max(m, n) + 1, 1024);
-	CU(h, h->hcells.reserve(stage_cells));
+	const bool have_cb = cb != nullptr;
+	if (have_cb) {
+		// pinned staging for rows / columns handed to the callbacks (nothing to stage without callbacks)
+		size_t stage_cells = std::max<size_t>((size_t)std::max(m, n) + 1, 1024);
+		CU(h, h->hcells.reserve(stage_cells));
+	}
 	if (reset_scalars(h, sw ? 0 : -kInf)) return 1;
 	CU(h, cudaMemcpyAsync(h->jobs.p, h->hjobs.data(), njobs * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
 	CU(h, cudaMemsetAsync(h->progress.p, 0, njobs * sizeof(int), h->stream));
@@ -496,7 +537,6 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	// ---- first row -> busH[j0..j1), first column -> left[0..m]   (AbstractDiagonalAligner.cpp:83-89,409-456)
 	Cell corner_col; corner_col.h = 0; corner_col.x = -kInf;
 	Cell corner_row = corner_col;
-	const bool have_cb = cb != nullptr;
 	if (cont) corner_col = h->cont_corner;
 	if (!cont && have_cb && cb->receive_first_column) cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(&corner_col), 1);
 	if (!cont && have_cb && cb->receive_first_row) cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(&corner_row), 1);
@@ -505,16 +545,16 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		// top border = last row of the previous chunk, already in busH
 	} else if (p->first_row_init == B200_INIT_ZEROES || !(have_cb && cb->receive_first_row)) {
 		int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
-		fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1 + p->reserved[1], 0);   // reserved[1]: column offset of a chained slice
+		fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1, 0);
 		h->stat_launches++;
-		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * (n + p->reserved[1]) - (type == B200_INIT_GAPS ? kGapOpen : 0);
+		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * n - (type == B200_INIT_GAPS ? kGapOpen : 0);
 	} else {
 		cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p), n);
 		first_row_tail = h->hcells.p[n - 1];
 		CU(h, cudaMemcpyAsync(h->busH.p + p->j0, h->hcells.p, (size_t)n * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 		CU(h, cudaStreamSynchronize(h->stream));
 	}
-	if (p->first_col_init != B200_INIT_ZEROES && !left_remote) {
+	if (p->first_col_init != B200_INIT_ZEROES) {
 		CU(h, h->left.reserve((size_t)m + 1));
 		if (have_cb && cb->receive_first_column) {
 			h->hcells.p[0] = corner_col;
@@ -532,18 +572,6 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	static const bool dbg = getenv("B200_DEBUG") != nullptr;
 	if (dbg) fprintf(stderr, "[b200] launch: %d strips, prune=%d track=%d kind=%d\n", njobs, (int)(p->prune && sw), track, kind);
 	// ---- the alignment itself: one persistent launch
-	if (chain) {
-		Cell* my_cells = reinterpret_cast<Cell*>(h->mg.block + 64);
-		if (left_remote) { h->ov.left = my_cells; h->ov.left_ready = h->mg.block + 0; }
-		if (right_remote) {
-			int* nb = h->mg.peers[h->mg.rank + 1];
-			h->ov.right = reinterpret_cast<Cell*>(nb + 64);
-			h->ov.right_ready = nb + 0;
-		}
-		h->ov.gbest = h->mg.block + 1;
-		h->ov.npeer = 0;
-		for (int r = 0; r < h->mg.world; r++) if (r != h->mg.rank) h->ov.peer_best[h->ov.npeer++] = h->mg.peers[r] + 1;
-	}
 	h->ov.prune = (p->prune && sw && track == 2 && kind == B200_KERNEL_S16X2) ? 1 : 0;
 	h->ov.prune_i1 = p->super_i1 > 0 ? p->super_i1 : p->i1;
 	h->ov.prune_j1 = p->super_j1 > 0 ? p->super_j1 : p->j1;
@@ -560,19 +588,20 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		h->ov.sra_done = h->sra_flags;
 	}
 	h->ov.mixed = !h->acgt_only;      // N / IUPAC bytes anywhere: PRMT variant (+ int32 strips); pure A/C/G/T: LUT variant
+	h->ov.no_right = !p->want_last_column;
 	CU(h, cudaEventRecord(h->ev0, h->stream));
 	int lrc = launch_strips(h, njobs, p->recurrence, track, kind, SH, true);
 	h->ov.sra_done = nullptr;
 	h->ov.mixed = false;
 	h->ov.prune = 0;
-	h->ov.left = nullptr; h->ov.right = nullptr; h->ov.left_ready = nullptr; h->ov.right_ready = nullptr; h->ov.gbest = nullptr; h->ov.npeer = 0;
+	h->ov.no_right = false;
 	if (lrc) return 1;
 	CU(h, cudaEventRecord(h->ev1, h->stream));
 	size_t rows_streamed = 0;
 	std::vector<int> sr_first_h(sr_ids.size(), 0);
 	if (stream_rows) {
 		// first-column H of every special row (its first dispatched cell), read before the kernel can finish
-		if (p->first_col_init != B200_INIT_ZEROES && !left_remote)
+		if (p->first_col_init != B200_INIT_ZEROES)
 			for (size_t k = 0; k < sr_ids.size(); k++)
 				CU(h, cudaMemcpyAsync(&sr_first_h[k], &h->left.p[sr_ids[k]].h, sizeof(int), cudaMemcpyDeviceToHost, h->copy_stream));
 		CU(h, cudaStreamSynchronize(h->copy_stream));
@@ -607,11 +636,6 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	float ms = 0;
 	CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
 
-	if (chain) {
-		// re-arm the exchange block for the next chained call; the caller barriers the ranks between calls
-		CU(h, cudaMemsetAsync(h->mg.block, 0, 2 * sizeof(int), h->stream));
-		CU(h, cudaStreamSynchronize(h->stream));
-	}
 	out->device_ms = ms;
 	out->strips = njobs;
 	out->kernel_launches = 1;
@@ -636,7 +660,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	if (have_cb) {
 		// first-column H values for the first cell of each dispatched row
 		int last_first_h = 0;
-		if (p->first_col_init != B200_INIT_ZEROES && !left_remote) {
+		if (p->first_col_init != B200_INIT_ZEROES) {
 			for (size_t k = rows_streamed; k < sr_ids.size(); k++)
 				CU(h, cudaMemcpy(&sr_first_h[k], &h->left.p[sr_ids[k]].h, sizeof(int), cudaMemcpyDeviceToHost));
 			CU(h, cudaMemcpy(&last_first_h, &h->left.p[m].h, sizeof(int), cudaMemcpyDeviceToHost));
@@ -655,7 +679,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 				cb->dispatch_row(cb->ctx, p->i1, reinterpret_cast<b200_cell*>(h->hcells.p), n);
 			}
 		}
-		if (cb->dispatch_column && p->want_last_column && !right_remote) {
+		if (cb->dispatch_column && p->want_last_column) {
 			CU(h, cudaMemcpy(h->hcells.p, h->right.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyDeviceToHost));
 			b200_cell fc; fc.h = first_row_tail.h; fc.x = -kInf;
 			if (!cont) cb->dispatch_column(cb->ctx, p->j1, &fc, 1);
@@ -852,19 +876,19 @@ extern "C" int b200_match_last_column(b200_handle* h, const b200_cell* buffer, c
 	out->found = 0; out->k = -1; out->score = 0; out->type = 0;
 	if (len == 0) return 0;
 	CU(h, cudaSetDevice(h->cfg.device));
-	CU(h, h->left.reserve(2 * (size_t)len + 2));
-	CU(h, h->scalars.reserve(8));
-	CU(h, h->hscalars.reserve(8));
-	Cell* dbuf = h->left.p; Cell* dbase = h->left.p + len;
+	CU(h, h->matchbuf.reserve(2 * (size_t)len + 2));
+	CU(h, h->matchflag.reserve(4));
+	CU(h, h->hmatchflag.reserve(4));
+	Cell* dbuf = h->matchbuf.p; Cell* dbase = h->matchbuf.p + len;
 	CU(h, cudaMemcpyAsync(dbuf, buffer, (size_t)len * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 	CU(h, cudaMemcpyAsync(dbase, base, (size_t)len * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
-	h->hscalars.p[0] = INT_MAX;
-	CU(h, cudaMemcpyAsync(h->scalars.p + 3, h->hscalars.p, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-	match_column_kernel<<<(len + 255) / 256, 256, 0, h->stream>>>(dbuf, dbase, len, goal, kGapOpen, h->scalars.p + 3);
+	h->hmatchflag.p[0] = INT_MAX;
+	CU(h, cudaMemcpyAsync(h->matchflag.p, h->hmatchflag.p, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	match_column_kernel<<<(len + 255) / 256, 256, 0, h->stream>>>(dbuf, dbase, len, goal, kGapOpen, h->matchflag.p);
 	h->stat_launches++;
-	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	CU(h, cudaMemcpyAsync(h->hmatchflag.p, h->matchflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
-	int code = h->hscalars.p[0];
+	int code = h->hmatchflag.p[0];
 	if (code != INT_MAX) {
 		int k = code >> 2, kindc = code & 3;
 		out->k = k;
@@ -876,19 +900,106 @@ extern "C" int b200_match_last_column(b200_handle* h, const b200_cell* buffer, c
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// multi-GPU chain
+// multi-GPU chain (block-cyclic column chunks, dataflow work queues)
 // ---------------------------------------------------------------------------------------------------------
 static_assert(sizeof(b200_ipc_handle) >= sizeof(cudaIpcMemHandle_t), "ipc handle size");
 
-extern "C" int b200_mgpu_export(b200_handle* h, int max_rows, b200_ipc_handle* out) {
-	if (!h) return 1;
-	if (!out || max_rows <= 0) { h->err = "b200_mgpu_export: bad arguments"; return 1; }
+namespace {
+
+// Exchange block of one GPU (peer-visible): [64 control ints][events u64 x cap_strips][queue int x cap_jobs][cells].
+//   ctrl[1], ctrl[2]  running best score shared by all GPUs; chained call e uses word 1 + (e & 1)
+//   ctrl[8]           queue tail (jobs pushed so far)
+constexpr int kCtlBest = 1, kCtlTail = 8, kCtlInts = 64;
+struct ExLayout { size_t off_events, off_queue, off_cells, bytes; };
+ExLayout ex_layout(long long cap_rows, long long cap_strips, long long cap_jobs) {
+	ExLayout l;
+	l.off_events = kCtlInts * sizeof(int);
+	l.off_queue = l.off_events + (size_t)cap_strips * sizeof(unsigned long long);
+	l.off_cells = (l.off_queue + (size_t)cap_jobs * sizeof(int) + 15) & ~(size_t)15;
+	l.bytes = l.off_cells + ((size_t)cap_rows + (size_t)cap_strips + 8) * sizeof(Cell);
+	return l;
+}
+long long strips_cap_for(long long max_rows) { return max_rows / 256 + 4096; }
+
+// (Re-)arm an exchange block: empty queue, event words at their start values.  GPU 0 owns chunk 0, whose jobs have no
+// left neighbour (one left event pre-counted); strip 0 has no strip above (top events pre-counted); job 0 = (strip 0,
+// chunk 0) is therefore ready from the start and pre-pushed.
+__global__ void chain_arm_kernel(int* block, size_t off_events, size_t off_queue, long long nstrips, long long njobs, int rank, int best_word) {
+	unsigned long long* ev = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(block) + off_events);
+	int* q = reinterpret_cast<int*>(reinterpret_cast<char*>(block) + off_queue);
+	const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+	for (long long k = tid; k < nstrips; k += nth) ev[k] = (rank == 0 ? (1ULL << 32) : 0ULL) | (k == 0 ? 0x40000000ULL : 0ULL);
+	for (long long k = tid; k < njobs; k += nth) q[k] = (rank == 0 && k == 0) ? 0 : -1;
+	if (tid == 0) {
+		block[kCtlTail] = rank == 0 ? 1 : 0;
+		if (best_word < 0) { block[kCtlBest] = INT_MIN; block[kCtlBest + 1] = INT_MIN; }
+		else block[kCtlBest + best_word] = INT_MIN;
+	}
+}
+
+int alloc_exchange(b200_handle* h, long long max_rows, long long max_jobs) {
 	CU(h, cudaSetDevice(h->cfg.device));
 	if (h->mg.block) { cudaFree(h->mg.block); h->mg.block = nullptr; }
-	size_t bytes = 64 * sizeof(int) + ((size_t)max_rows + 2) * sizeof(Cell);
-	CU(h, cudaMalloc((void**)&h->mg.block, bytes));
-	CU(h, cudaMemset(h->mg.block, 0, bytes));
-	h->mg.max_rows = (size_t)max_rows;
+	h->mg.cap_rows = max_rows; h->mg.cap_strips = strips_cap_for(max_rows); h->mg.cap_jobs = std::max<long long>(max_jobs, 1);
+	const ExLayout l = ex_layout(h->mg.cap_rows, h->mg.cap_strips, h->mg.cap_jobs);
+	CU(h, cudaMalloc((void**)&h->mg.block, l.bytes));
+	CU(h, cudaMemset(h->mg.block, 0, l.off_cells));
+	return 0;
+}
+
+int arm_exchange(b200_handle* h, long long nstrips, long long njobs, int best_word) {
+	const ExLayout l = ex_layout(h->mg.cap_rows, h->mg.cap_strips, h->mg.cap_jobs);
+	chain_arm_kernel<<<512, 256, 0, h->stream>>>(h->mg.block, l.off_events, l.off_queue, nstrips, njobs, h->mg.rank, best_word);
+	h->stat_launches++;
+	CU(h, cudaGetLastError());
+	return 0;
+}
+
+// Column chunks of a chained partition.  chunk_cols > 0: block-cyclic chunks of that width (the last one may be
+// narrower).  chunk_cols == 0: a width that gives every GPU about 16 chunks (load balance under pruning, short pipeline
+// fill) within [32 Ki, 1 Mi] columns.  chunk_cols < 0: one contiguous slice per GPU with the integer arithmetic of the
+// reference's --split (C/libmasa/libmasa.cpp:632-635).
+void chain_bounds(int n, int world, int chunk_cols, std::vector<int>& b) {
+	b.clear();
+	if (chunk_cols < 0) {
+		for (int r = 0; r <= world; r++) b.push_back((int)((long long)n * r / world));
+		// drop empty slices (n < world)
+		std::vector<int> u; u.push_back(0);
+		for (size_t k = 1; k < b.size(); k++) if (b[k] > u.back()) u.push_back(b[k]);
+		b.swap(u);
+		return;
+	}
+	long long w = chunk_cols;
+	if (w == 0) {
+		w = (long long)n / ((long long)world * 16);
+		w = std::max<long long>(32768, std::min<long long>(w, 1 << 20));
+		w = (w + 1023) / 1024 * 1024;
+	}
+	for (long long j = 0; j < n; j += w) b.push_back((int)j);
+	b.push_back(n);
+}
+
+}  // namespace
+
+extern "C" int b200_chain_plan(const b200_partition* p, int world, b200_chain_info* out) {
+	if (!p || !out || world < 1 || world > 8) return 1;
+	const int m = p->i1 - p->i0, n = p->j1 - p->j0;
+	if (m <= 0 || n <= 0) return 1;
+	std::vector<int> b;
+	chain_bounds(n, world, p->reserved[1], b);
+	memset(out, 0, sizeof(*out));
+	out->chunks = (int)b.size() - 1;
+	out->chunk_cols = b.size() > 1 ? b[1] - b[0] : n;
+	out->chunks_per_gpu = (out->chunks + world - 1) / world;
+	out->max_strips = strips_cap_for(m);
+	out->max_jobs = (long long)out->chunks_per_gpu * out->max_strips;
+	return 0;
+}
+
+extern "C" int b200_mgpu_export(b200_handle* h, long long max_rows, long long max_jobs, b200_ipc_handle* out) {
+	if (!h) return 1;
+	if (!out || max_rows <= 0 || max_jobs <= 0) { h->err = "b200_mgpu_export: bad arguments"; return 1; }
+	if (alloc_exchange(h, max_rows, max_jobs)) return 1;
 	cudaIpcMemHandle_t ih;
 	CU(h, cudaIpcGetMemHandle(&ih, h->mg.block));
 	memset(out, 0, sizeof(*out));
@@ -909,17 +1020,413 @@ extern "C" int b200_mgpu_connect(b200_handle* h, int rank, int world, const b200
 		CU(h, cudaIpcOpenMemHandle(&ptr, ih, cudaIpcMemLazyEnablePeerAccess));
 		h->mg.peers[r] = reinterpret_cast<int*>(ptr);
 	}
-	h->mg.rank = rank; h->mg.world = world; h->mg.connected = true;
+	h->mg.rank = rank; h->mg.world = world; h->mg.connected = true; h->mg.ipc = true; h->mg.epoch = 0;
+	if (arm_exchange(h, h->mg.cap_strips, h->mg.cap_jobs, -1)) return 1;
+	CU(h, cudaStreamSynchronize(h->stream));
 	return 0;
 }
 
 extern "C" int b200_mgpu_disconnect(b200_handle* h) {
 	if (!h) return 1;
-	if (h->mg.connected)
+	if (h->mg.connected && h->mg.ipc)
 		for (int r = 0; r < h->mg.world; r++)
 			if (r != h->mg.rank && h->mg.peers[r]) cudaIpcCloseMemHandle(h->mg.peers[r]);
 	h->mg.connected = false;
-	if (h->mg.block) { cudaFree(h->mg.block); h->mg.block = nullptr; }
+	if (h->mg.block) { cudaSetDevice(h->cfg.device); cudaFree(h->mg.block); h->mg.block = nullptr; }
+	h->mg.strips.release(); h->mg.chunks.release(); h->mg.hrow.release();
+	return 0;
+}
+
+// One chained alignment over the `nlocal` handles of THIS process (1 with one process per GPU: the other GPUs run the
+// same call in their own processes; all of them with b200_group).  Every handle is connected to the same chain and
+// holds both sequences.  Callers separate consecutive chained calls by a barrier over all ranks.
+static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition* p, const b200_callbacks* cb, b200_result* out) {
+	b200_handle* h0 = hs[0];
+	memset(out, 0, sizeof(*out));
+	const int m = p->i1 - p->i0, n = p->j1 - p->j0;
+	const int world = h0->mg.world;
+#define FAIL(msg) do { h0->err = (msg); return 1; } while (0)
+	for (int q = 0; q < nlocal; q++) {
+		b200_handle* h = hs[q];
+		if (!h->mg.connected || h->mg.world != world) FAIL("chained alignment: b200_mgpu_connect / b200_group_create was not called on every handle");
+		if (m <= 0 || n <= 0 || p->i0 < 0 || p->j0 < 0 || p->i1 > h->n0 || p->j1 > h->n1) FAIL("chained alignment: partition outside the sequences");
+		if ((long long)m > h->mg.cap_rows) FAIL("chained alignment: more rows than the exchange block was exported for");
+	}
+	if (p->reserved[0] & B200_CONT_CHUNK) FAIL("chained alignment: B200_CONT_CHUNK is not supported");
+	const bool all_local = nlocal == world;
+	const bool sw = p->recurrence == B200_SMITH_WATERMAN;
+	const int track = p->want_best_score ? 2 : 0;
+	const bool have_cb = cb != nullptr;
+	static const bool dbg = getenv("B200_DEBUG") != nullptr;
+
+	// ---- plan: strips (identical everywhere), chunks (owner = index mod world)
+	int bh = p->block_height > 0 ? p->block_height : 4 * std::min(128, n);
+	std::vector<int> sr_ids;
+	if (p->want_special_rows) special_row_ids(m, bh, p->special_row_interval, sr_ids);
+	std::vector<StripRow> srows;
+	bool any_s16 = false;
+	build_strips(h0, p, m, sr_ids, srows, any_s16);
+	const int S = (int)srows.size();
+	const int kind = any_s16 ? B200_KERNEL_S16X2 : B200_KERNEL_S32;
+	std::vector<int> bounds;
+	chain_bounds(n, world, p->reserved[1], bounds);
+	const int C = (int)bounds.size() - 1;
+	if ((long long)S > h0->mg.cap_strips) FAIL("chained alignment: more strips than the exchange block was exported for");
+	const int last_owner = (C - 1) % world;
+	int chunk_max = 0;
+	for (int c = 0; c < C; c++) chunk_max = std::max(chunk_max, bounds[c + 1] - bounds[c]);
+
+	struct Local { std::vector<ChunkCol> chunks; long long cols = 0; long long njobs = 0; std::vector<int> first_h; };
+	std::vector<Local> loc(nlocal);
+	for (int q = 0; q < nlocal; q++) {
+		b200_handle* h = hs[q];
+		Local& L = loc[q];
+		for (int c = h->mg.rank; c < C; c += world) {
+			ChunkCol cc; cc.j0 = p->j0 + bounds[c]; cc.cols = bounds[c + 1] - bounds[c]; cc.cum = (int)L.cols; cc.gidx = c;
+			L.chunks.push_back(cc);
+			L.cols += cc.cols;
+		}
+		L.njobs = (long long)L.chunks.size() * S;
+		if (L.njobs > h->mg.cap_jobs) FAIL("chained alignment: more jobs than the exchange block was exported for (b200_chain_plan gives the size)");
+		if (L.njobs > 0x7fffffffLL) FAIL("chained alignment: too many jobs; use wider chunks");
+	}
+
+	// ---- first row / first column from the caller (host side, once)
+	Cell corner_col; corner_col.h = 0; corner_col.x = -kInf;
+	Cell corner_row = corner_col;
+	b200_handle* hr0 = nullptr;                    // the local handle that is rank 0 (owner of chunk 0), if any
+	b200_handle* hlast = nullptr;                  // the local handle that owns the last chunk, if any
+	for (int q = 0; q < nlocal; q++) { if (hs[q]->mg.rank == 0) hr0 = hs[q]; if (hs[q]->mg.rank == last_owner) hlast = hs[q]; }
+	if (have_cb && cb->receive_first_column && hr0) cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(&corner_col), 1);
+	if (have_cb && cb->receive_first_row) cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(&corner_row), 1);
+	Cell first_row_tail = corner_row;
+	const bool custom_row = !(p->first_row_init == B200_INIT_ZEROES || !(have_cb && cb->receive_first_row));
+	const bool need_rows = have_cb && cb->dispatch_row && (!sr_ids.empty() || p->want_last_row);
+	if (custom_row || need_rows) {
+		CU(h0, cudaSetDevice(h0->cfg.device));
+		CU(h0, h0->mg.hrow.reserve((size_t)n + 8));
+	}
+	if (custom_row) {
+		cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(h0->mg.hrow.p), n);
+		first_row_tail = h0->mg.hrow.p[n - 1];
+	} else {
+		const int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
+		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * n - (type == B200_INIT_GAPS ? kGapOpen : 0);
+	}
+
+	// ---- per GPU: buffers, tables, borders, launch
+	const bool stream_rows = have_cb && cb->dispatch_row && !sr_ids.empty();
+	for (int q = 0; q < nlocal; q++) {
+		b200_handle* h = hs[q];
+		Local& L = loc[q];
+		const int K = (int)L.chunks.size();
+		CU(h, cudaSetDevice(h->cfg.device));
+		CU(h, h->mg.strips.reserve(S));
+		CU(h, h->mg.chunks.reserve(std::max(K, 1)));
+		CU(h, h->progress.reserve(S));
+		CU(h, h->results.reserve(S));
+		CU(h, h->hresults.reserve(S));
+		if (!sr_ids.empty()) CU(h, h->sra.reserve(sr_ids.size() * (size_t)std::max<long long>(L.cols, 1)));
+		if (p->want_last_column && h == hlast) CU(h, h->right.reserve((size_t)m + 1));
+		if (reset_scalars(h, INT_MIN)) { h0->err = h->err; return 1; }
+		CU(h, cudaMemcpyAsync(h->mg.strips.p, srows.data(), S * sizeof(StripRow), cudaMemcpyHostToDevice, h->stream));
+		if (K) CU(h, cudaMemcpyAsync(h->mg.chunks.p, L.chunks.data(), K * sizeof(ChunkCol), cudaMemcpyHostToDevice, h->stream));
+		CU(h, cudaMemsetAsync(h->progress.p, 0, S * sizeof(int), h->stream));
+		{
+			// results start as "none": strips whose jobs all live on other GPUs keep this value
+			fill_const_kernel<<<(2 * S + 255) / 256, 256, 0, h->stream>>>(reinterpret_cast<Cell*>(h->results.p), 2LL * S, -kInf, -1);
+			h->stat_launches++;
+		}
+		if (custom_row) {
+			for (const ChunkCol& cc : L.chunks)
+				CU(h, cudaMemcpyAsync(h->busH.p + cc.j0, h0->mg.hrow.p + (cc.j0 - p->j0), (size_t)cc.cols * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+		} else {
+			const int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
+			fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1, 0);
+			h->stat_launches++;
+		}
+		if (h == hr0 && p->first_col_init != B200_INIT_ZEROES) {
+			CU(h, h->left.reserve((size_t)m + 1));
+			if (have_cb && cb->receive_first_column) {
+				CU(h, h->hcells.reserve((size_t)m + 2));
+				h->hcells.p[0] = corner_col;
+				cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p + 1), m);
+				CU(h, cudaMemcpyAsync(h->left.p, h->hcells.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
+			} else {
+				const int type = p->first_col_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_col_init;
+				fill_cells_kernel<<<(m + 1 + 255) / 256, 256, 0, h->stream>>>(h->left.p, (long long)m + 1, type, 0, 0);
+				h->stat_launches++;
+			}
+		}
+		// every allocation happens before the first launch: cudaHostAlloc / cudaMalloc may wait for running kernels, and a
+		// persistent kernel that waits for a neighbour which has not been launched yet would never finish
+		if (stream_rows && h->sra_flags_cap < sr_ids.size()) {
+			if (h->sra_flags) cudaFreeHost(h->sra_flags);
+			h->sra_flags = nullptr; h->sra_flags_cap = 0;
+			CU(h, cudaHostAlloc((void**)&h->sra_flags, (sr_ids.size() + 64) * sizeof(int), cudaHostAllocMapped));
+			h->sra_flags_cap = sr_ids.size() + 64;
+		}
+		if (h == hlast && have_cb && cb->dispatch_column && p->want_last_column) CU(h, h->hcells.reserve((size_t)m + 2));
+		CU(h, cudaStreamSynchronize(h->stream));          // pinned staging is reused below
+	}
+	for (int q = 0; q < nlocal; q++) {
+		b200_handle* h = hs[q];
+		Local& L = loc[q];
+		CU(h, cudaSetDevice(h->cfg.device));
+		if (stream_rows) memset(h->sra_flags, 0, sr_ids.size() * sizeof(int));
+		const ExLayout l = ex_layout(h->mg.cap_rows, h->mg.cap_strips, h->mg.cap_jobs);
+		const int nxr = (h->mg.rank + 1) % world;
+		char* mine = reinterpret_cast<char*>(h->mg.block);
+		char* next = reinterpret_cast<char*>(h->mg.peers[nxr]);
+		ChainParams& ch = h->ov.chain;
+		memset(&ch, 0, sizeof(ch));
+		ch.enabled = 1; ch.world = world; ch.nstrips = S; ch.nchunks_local = (int)L.chunks.size(); ch.nchunks_total = C;
+		ch.left_zero = p->first_col_init == B200_INIT_ZEROES ? 1 : 0;
+		ch.local_cols = L.cols;
+		ch.strips = h->mg.strips.p; ch.chunks = h->mg.chunks.p;
+		ch.queue = reinterpret_cast<int*>(mine + l.off_queue); ch.q_tail = h->mg.block + kCtlTail;
+		ch.events = reinterpret_cast<unsigned long long*>(mine + l.off_events);
+		ch.my_cells = reinterpret_cast<const Cell*>(mine + l.off_cells);
+		ch.nx_queue = reinterpret_cast<int*>(next + l.off_queue); ch.nx_tail = h->mg.peers[nxr] + kCtlTail;
+		ch.nx_events = reinterpret_cast<unsigned long long*>(next + l.off_events);
+		ch.nx_cells = reinterpret_cast<Cell*>(next + l.off_cells);
+		const int word = kCtlBest + (int)(h->mg.epoch & 1u);
+		h->ov.gbest = h->mg.block + word;
+		h->ov.npeer = 0;
+		for (int r = 0; r < world; r++) if (r != h->mg.rank) h->ov.peer_best[h->ov.npeer++] = h->mg.peers[r] + word;
+		h->ov.prune = (p->prune && sw && track == 2 && kind == B200_KERNEL_S16X2) ? 1 : 0;
+		h->ov.prune_i1 = p->super_i1 > 0 ? p->super_i1 : p->i1;
+		h->ov.prune_j1 = p->super_j1 > 0 ? p->super_j1 : p->j1;
+		h->ov.sra_done = stream_rows ? h->sra_flags : nullptr;
+		h->ov.mixed = !h->acgt_only;
+		h->ov.no_right = !(p->want_last_column && h == hlast);
+		h->ov.chunk_cols_max = chunk_max;
+		if (dbg) fprintf(stderr, "[b200] chain rank %d/%d: %d strips x %d chunks (of %d, <= %d columns), prune=%d kind=%d\n", h->mg.rank, world, S, (int)L.chunks.size(), C, chunk_max, h->ov.prune, kind);
+		int lrc = 0;
+		CU(h, cudaEventRecord(h->ev0, h->stream));
+		if (L.njobs > 0) lrc = launch_strips(h, (int)L.njobs, p->recurrence, track, kind, kSH16F, true);
+		CU(h, cudaEventRecord(h->ev1, h->stream));
+		memset(&ch, 0, sizeof(ch));
+		h->ov.gbest = nullptr; h->ov.npeer = 0; h->ov.prune = 0; h->ov.sra_done = nullptr; h->ov.mixed = false; h->ov.no_right = false; h->ov.chunk_cols_max = 0;
+		if (lrc) { h0->err = h->err; return 1; }
+	}
+
+	// ---- while the kernels run: stream the special rows out (a row is complete once every local GPU has flagged it)
+	// Rows are handed over as: [first-column cell, when rank 0 is local] then the chunks owned by local GPUs in column
+	// order -- i.e. the whole row in one piece when all GPUs are local, exactly like the single-GPU path.
+	std::vector<int> sr_first_h(sr_ids.size() + 1, 0);           // + the last row
+	if (need_rows && hr0 && p->first_col_init != B200_INIT_ZEROES) {
+		CU(hr0, cudaSetDevice(hr0->cfg.device));
+		for (size_t k = 0; k < sr_ids.size(); k++)
+			CU(hr0, cudaMemcpyAsync(&sr_first_h[k], &hr0->left.p[sr_ids[k]].h, sizeof(int), cudaMemcpyDeviceToHost, hr0->copy_stream));
+		CU(hr0, cudaMemcpyAsync(&sr_first_h[sr_ids.size()], &hr0->left.p[m].h, sizeof(int), cudaMemcpyDeviceToHost, hr0->copy_stream));
+		CU(hr0, cudaStreamSynchronize(hr0->copy_stream));
+	}
+	// copy row `k` of the local special-rows areas (k < 0: the last row, from busH) into the staging row and dispatch it
+	auto dispatch_row = [&](long long k, int row_id, int first_h) -> int {
+		for (int q = 0; q < nlocal; q++) {
+			b200_handle* h = hs[q];
+			CU(h, cudaSetDevice(h->cfg.device));
+			for (const ChunkCol& cc : loc[q].chunks) {
+				const Cell* src = k >= 0 ? h->sra.p + (size_t)k * (size_t)loc[q].cols + cc.cum : h->busH.p + cc.j0;
+				CU(h, cudaMemcpyAsync(h0->mg.hrow.p + (cc.j0 - p->j0), src, (size_t)cc.cols * sizeof(Cell), cudaMemcpyDeviceToHost, h->copy_stream));
+			}
+		}
+		for (int q = 0; q < nlocal; q++) { CU(hs[q], cudaSetDevice(hs[q]->cfg.device)); CU(hs[q], cudaStreamSynchronize(hs[q]->copy_stream)); }
+		if (hr0) { b200_cell fc; fc.h = first_h; fc.x = -kInf; cb->dispatch_row(cb->ctx, row_id, &fc, 1); }
+		if (all_local) cb->dispatch_row(cb->ctx, row_id, reinterpret_cast<b200_cell*>(h0->mg.hrow.p), n);
+		else
+			for (int c = 0; c < C; c++)
+				for (int q = 0; q < nlocal; q++)
+					if (c % world == hs[q]->mg.rank)
+						cb->dispatch_row(cb->ctx, row_id, reinterpret_cast<b200_cell*>(h0->mg.hrow.p + bounds[c]), bounds[c + 1] - bounds[c]);
+		return 0;
+	};
+	size_t rows_streamed = 0;
+	if (stream_rows) {
+		while (rows_streamed < sr_ids.size()) {
+			bool ready = true, running = false;
+			for (int q = 0; q < nlocal; q++) {
+				if (loc[q].chunks.empty()) continue;
+				if (!((volatile int*)hs[q]->sra_flags)[rows_streamed]) ready = false;
+				cudaSetDevice(hs[q]->cfg.device);
+				if (cudaStreamQuery(hs[q]->stream) == cudaErrorNotReady) running = true;
+			}
+			if (!ready) {
+				if (!running) break;                               // kernels over (or failed): the rest is handled below
+				struct timespec ts = {0, 20000}; nanosleep(&ts, nullptr);
+				continue;
+			}
+			if (dispatch_row((long long)rows_streamed, p->i0 + sr_ids[rows_streamed], sr_first_h[rows_streamed])) return 1;
+			rows_streamed++;
+		}
+	}
+
+	// ---- completion
+	int stop = 0;
+	b200_score best; best.score = -kInf; best.i = -1; best.j = -1;
+	for (int q = 0; q < nlocal; q++) {
+		b200_handle* h = hs[q];
+		CU(h, cudaSetDevice(h->cfg.device));
+		if (track) CU(h, cudaMemcpyAsync(h->hresults.p, h->results.p, S * sizeof(Score3), cudaMemcpyDeviceToHost, h->stream));
+		CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+	}
+	for (int q = 0; q < nlocal; q++) {
+		b200_handle* h = hs[q];
+		CU(h, cudaSetDevice(h->cfg.device));
+		cudaError_t e = cudaStreamSynchronize(h->stream);
+		if (e != cudaSuccess) { h0->err = std::string("chained alignment, GPU ") + std::to_string(h->mg.rank) + ": " + cudaGetErrorString(e); return 1; }
+		if (h->hscalars.p[2] != 0 && stop == 0) stop = h->hscalars.p[2];
+		float ms = 0;
+		CU(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+		b200_result& r = h->last_chain;
+		memset(&r, 0, sizeof(r));
+		r.device_ms = ms; r.strips = S; r.kernel_launches = loc[q].njobs > 0 ? 1 : 0; r.kernel_used = kind;
+		r.cells = (long long)*reinterpret_cast<unsigned long long*>(h->hscalars.p + 4);
+		r.cells_total = (long long)m * loc[q].cols;
+		r.best.score = -kInf; r.best.i = r.best.j = -1;
+		if (track)
+			for (int k = 0; k < S; k++) {
+				const Score3& s = h->hresults.p[k];
+				if (s.i >= 0 && (s.score > r.best.score || (s.score == r.best.score && (s.i < r.best.i || (s.i == r.best.i && s.j < r.best.j))))) {
+					r.best.score = s.score; r.best.i = s.i; r.best.j = s.j;
+				}
+			}
+		h->stat_cells += r.cells;
+		out->cells += r.cells;
+		out->device_ms = std::max(out->device_ms, (double)ms);
+		out->kernel_launches += r.kernel_launches;
+		if (r.best.i >= 0 && (r.best.score > best.score || (r.best.score == best.score && (r.best.i < best.i || (r.best.i == best.i && r.best.j < best.j))))) best = r.best;
+		// re-arm this GPU's exchange block for the next chained call (everything that writes into it has finished: its
+		// only producers are the jobs on its left, all consumed; running-best pushes of slower peers go to this call's
+		// word, the NEXT call's word is reset here)
+		h->mg.epoch++;
+		if (arm_exchange(h, S, loc[q].njobs, (int)(h->mg.epoch & 1u))) { h0->err = h->err; return 1; }
+		CU(h, cudaStreamSynchronize(h->stream));
+	}
+	if (stop != 0) { h0->err = "strip kernel watchdog: a border dependency did not advance (code " + std::to_string(stop) + ")"; return 5; }
+	out->strips = S; out->kernel_used = kind; out->cells_total = (long long)m * n; out->best = best;
+	out->reserved[0] = C; out->reserved[1] = chunk_max;
+
+	// ---- remaining artefacts
+	if (have_cb) {
+		if (cb->dispatch_row) {
+			for (size_t k = rows_streamed; k < sr_ids.size(); k++)
+				if (dispatch_row((long long)k, p->i0 + sr_ids[k], sr_first_h[k])) return 1;
+			if (p->want_last_row && dispatch_row(-1, p->i1, sr_first_h[sr_ids.size()])) return 1;
+		}
+		if (cb->dispatch_column && p->want_last_column && hlast) {
+			b200_handle* h = hlast;
+			CU(h, cudaSetDevice(h->cfg.device));
+			CU(h, cudaMemcpy(h->hcells.p, h->right.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyDeviceToHost));
+			b200_cell fc; fc.h = first_row_tail.h; fc.x = -kInf;
+			cb->dispatch_column(cb->ctx, p->j1, &fc, 1);
+			for (int r = 0; r < m; r += bh) {
+				int len = std::min(bh, m - r);
+				cb->dispatch_column(cb->ctx, p->j1, reinterpret_cast<b200_cell*>(h->hcells.p + 1 + r), len);
+				if (cb->must_continue && !cb->must_continue(cb->ctx)) break;
+			}
+		}
+		if (cb->dispatch_score && track && best.i >= 0) cb->dispatch_score(cb->ctx, best);
+	}
+#undef FAIL
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// in-process group: one host thread drives several GPUs (the multi-GPU mode of build/cudalign)
+// ---------------------------------------------------------------------------------------------------------
+struct b200_group {
+	std::vector<b200_handle*> hs;
+	std::string err;
+};
+
+extern "C" const char* b200_group_last_error(const b200_group* g) {
+	if (!g) return g_create_error.c_str();
+	if (!g->err.empty()) return g->err.c_str();
+	return g->hs.empty() ? "" : g->hs[0]->err.c_str();
+}
+
+extern "C" void b200_group_destroy(b200_group* g) {
+	if (!g) return;
+	for (b200_handle* h : g->hs) b200_destroy(h);
+	delete g;
+}
+
+extern "C" int b200_group_create(const int* devices, int n, const b200_config* cfg, long long max_rows, long long max_jobs, b200_group** out) {
+	if (!out) return 1;
+	*out = nullptr;
+	if (!devices || n < 1 || n > 8 || max_rows <= 0 || max_jobs <= 0) { g_create_error = "b200_group_create: bad arguments (1..8 devices)"; return 1; }
+	b200_group* g = new b200_group();
+	for (int r = 0; r < n; r++) {
+		b200_config c;
+		memset(&c, 0, sizeof(c));
+		if (cfg) c = *cfg;
+		c.device = devices[r];
+		// test hook: several ranks on ONE device must share its warp slots to be co-resident (tests/test_chain_gpu.py)
+		if (const char* e = getenv("B200_GROUP_WARPS_PER_SM")) c.warps_per_sm = atoi(e);
+		b200_handle* h = nullptr;
+		int rc = b200_create(&c, &h);
+		if (rc) { b200_group_destroy(g); return rc; }
+		g->hs.push_back(h);
+	}
+	// peer access between every pair (NVLink / NVSwitch), exchange blocks, chain wiring
+	for (int r = 0; r < n; r++) {
+		b200_handle* h = g->hs[r];
+		cudaSetDevice(h->cfg.device);
+		for (int q = 0; q < n; q++) {
+			if (q == r || g->hs[q]->cfg.device == h->cfg.device) continue;
+			int can = 0;
+			cudaDeviceCanAccessPeer(&can, h->cfg.device, g->hs[q]->cfg.device);
+			if (!can) { g_create_error = "b200_group_create: no peer access between GPU " + std::to_string(h->cfg.device) + " and GPU " + std::to_string(g->hs[q]->cfg.device); b200_group_destroy(g); return 3; }
+			cudaError_t e = cudaDeviceEnablePeerAccess(g->hs[q]->cfg.device, 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g_create_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e); b200_group_destroy(g); return 3; }
+			cudaGetLastError();
+		}
+		if (alloc_exchange(h, max_rows, max_jobs)) { g_create_error = h->err; b200_group_destroy(g); return 3; }
+	}
+	for (int r = 0; r < n; r++) {
+		b200_handle* h = g->hs[r];
+		for (int q = 0; q < n; q++) h->mg.peers[q] = g->hs[q]->mg.block;
+		h->mg.rank = r; h->mg.world = n; h->mg.connected = true; h->mg.ipc = false; h->mg.epoch = 0;
+		cudaSetDevice(h->cfg.device);
+		if (arm_exchange(h, h->mg.cap_strips, h->mg.cap_jobs, -1) || cudaStreamSynchronize(h->stream) != cudaSuccess) { g_create_error = "b200_group_create: cannot initialise the exchange block: " + h->err; b200_group_destroy(g); return 3; }
+	}
+	*out = g;
+	return 0;
+}
+
+extern "C" int b200_group_size(const b200_group* g) { return g ? (int)g->hs.size() : 0; }
+extern "C" b200_handle* b200_group_handle(b200_group* g, int rank) { return (g && rank >= 0 && rank < (int)g->hs.size()) ? g->hs[rank] : nullptr; }
+
+extern "C" int b200_group_set_sequences(b200_group* g, const char* seq0, int seq0_len, const char* seq1, int seq1_len) {
+	if (!g) return 1;
+	g->err.clear();
+	for (b200_handle* h : g->hs) {
+		int rc = b200_set_sequences(h, seq0, seq0_len, seq1, seq1_len);
+		if (rc) { g->err = h->err; return rc; }
+	}
+	return 0;
+}
+
+extern "C" int b200_group_align_partition(b200_group* g, const b200_partition* p, const b200_callbacks* cb, b200_result* out) {
+	if (!g) return 1;
+	g->err.clear();
+	if (!p || !out) { g->err = "b200_group_align_partition: bad arguments"; return 1; }
+	int rc = chain_align(g->hs.data(), (int)g->hs.size(), p, cb, out);
+	if (rc) g->err = g->hs[0]->err;
+	return rc;
+}
+
+extern "C" int b200_group_rank_result(const b200_group* g, int rank, b200_result* out) {
+	if (!g || !out || rank < 0 || rank >= (int)g->hs.size()) return 1;
+	*out = g->hs[rank]->last_chain;
+	return 0;
+}
+
+extern "C" int b200_last_chain_result(const b200_handle* h, b200_result* out) {
+	if (!h || !out) return 1;
+	*out = h->last_chain;
 	return 0;
 }
 

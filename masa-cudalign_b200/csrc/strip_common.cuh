@@ -32,6 +32,8 @@ enum JobFlags : int {
 	JOB_PRUNED    = 2,      // do not compute: write -INF to the right border (CUDAligner.cu:950-960 semantics)
 	JOB_TOP_MINF  = 4,      // treat the top border as -INF instead of reading busH (strip above was pruned)
 	JOB_S32       = 8,      // rows of this strip contain a non-ACGT byte: run it with the exact int32 code path
+	JOB_RIGHT_PEER = 16,    // chain mode: right_off indexes the exchange cells of the next GPU, not StripParams::right
+	JOB_LEFT_XCHG = 32,     // chain mode: left_off indexes our exchange cells (border delivered by the previous GPU), not StripParams::left
 };
 
 struct StripJob {
@@ -43,6 +45,46 @@ struct StripJob {
 	int right_off;          // cell index of slot 0 of our right border in StripParams::right, or -1
 	long long sra_off;      // cell index in StripParams::sra where column j0 of our bottom row goes, or -1
 	long long sra_index;    // which special row this strip's bottom row is (index into StripParams::sra_done)
+};
+
+// ---- block-cyclic multi-GPU chain ---------------------------------------------------------
+// seq1 is cut into column CHUNKS; chunk c belongs to GPU (c mod world).  A job is (strip r, local chunk k); it may
+// start when (r, c-1) has delivered its right border (left event, from the previous GPU over NVLink) and (r-1, c) has
+// published its first columns (top event, same GPU).  Each strip has one 64-bit event word {left events : 32 | top
+// events : 32} on the GPU that owns the job; whoever completes the pair pushes the job into that GPU's work queue.
+// Warps pop jobs from the queue, so a resident warp never waits for a job that cannot start yet.
+struct StripRow {            // one horizontal strip of the partition (identical on every GPU)
+	int i0, rows;            // first row (index into seq0), number of rows
+	int flags;               // JOB_S32
+	int left_off;            // rows above this strip (offset of its slot 0 in a first/last-column array)
+	int sra_row;             // index of the special row this strip's bottom row is, or -1
+	int pad[3];
+};
+struct ChunkCol {            // one column chunk owned by this GPU
+	int j0, cols;            // first column (index into seq1), number of columns
+	int cum;                 // columns of this GPU's earlier chunks (offset in the cumulative progress counters / local SRA rows)
+	int gidx;                // global chunk index c
+};
+struct ChainParams {
+	int enabled;
+	int world;               // GPUs in the chain
+	int nstrips;             // S
+	int nchunks_local;       // K: chunks owned by this GPU
+	int nchunks_total;       // C
+	int left_zero;           // the partition's first column is the constant (H=0, E=-INF)
+	long long local_cols;    // sum of this GPU's chunk widths (row pitch of the local special-rows area)
+	const StripRow* strips;  // [S]
+	const ChunkCol* chunks;  // [K]
+	// this GPU's exchange block (peer-visible memory)
+	int* queue;              // [K*S] job ids in push order, -1 = not pushed yet
+	int* q_tail;             // push counter
+	unsigned long long* events;   // [S] {left events << 32 | top events}
+	const Cell* my_cells;    // left borders delivered by the previous GPU: strip r at [left_off + r, +rows+1)
+	// the exchange block of the GPU that owns the chunks on our right (peer memory; our own block when world == 1)
+	int* nx_queue;
+	int* nx_tail;
+	unsigned long long* nx_events;
+	Cell* nx_cells;
 };
 
 struct StripParams {
@@ -60,8 +102,6 @@ struct StripParams {
 	int* global_best;       // running best score of the whole partition (atomicMax)
 	unsigned long long* cells_done;   // statistics
 	int* stop_flag;         // non-zero asks the kernel to stop (set by a spin-wait watchdog: no hung GPU on a protocol bug)
-	const int* left_ready;  // multi-GPU: rows of our left border published by the previous GPU (system scope), or NULL
-	int* right_ready;       // multi-GPU: row counter in the NEXT GPU's exchange block (peer memory), or NULL
 	int* peer_best[8];      // multi-GPU: running-best words of the other GPUs (peer memory)
 	int n_peer_best;
 	int* sra_done;          // host-mapped flags, one per special row: set when the row is complete in the device SRA, or NULL
@@ -70,7 +110,25 @@ struct StripParams {
 	int prune;              // SW block pruning inside the strips (needs track == 2)
 	int prune_i1, prune_j1; // end of the (super) partition: bounds of the distance term of the pruning test
 	int opt;                // StripOpt bits: protocol variants of the strip chain (engine default, B200_OPT overrides)
+	long long watchdog_ns;  // a dependency that shows no progress for this long stops the kernel with an error (0 = never)
+	int test_delay_ms;      // test hook: the first job sleeps this long before it starts (tests/test_watchdog_gpu.py)
+	ChainParams chain;
 };
+
+// A job as the kernels see it: geometry plus where its progress counter and result live.  Kept small on purpose: the
+// packed kernel runs at the 128-register limit, so everything the rare paths need is re-derived from `job` there.
+struct JobCtx {
+	StripJob jb;            // jb.dep = index of the progress counter of the strip above, or -1
+	int job;                // job id (chain mode: k * nstrips + r)
+	int pidx;               // index of our progress counter and of our result (chain mode: the strip, otherwise the job)
+	int prog_base;          // value of the counters that corresponds to column 0 of this job (chain: cumulative over chunks)
+};
+__device__ __forceinline__ const Cell* left_border(const StripParams& p, const JobCtx& c) {
+	return ((c.jb.flags & JOB_LEFT_XCHG) ? p.chain.my_cells : p.left) + c.jb.left_off;
+}
+__device__ __forceinline__ Cell* right_border(const StripParams& p, const JobCtx& c) {      // only when jb.right_off >= 0
+	return ((c.jb.flags & JOB_RIGHT_PEER) ? p.chain.nx_cells : p.right) + c.jb.right_off;
+}
 
 // Variants of the strip-chaining protocol (all exact; they only change how often the chain synchronises).
 enum StripOpt : int {
@@ -102,16 +160,43 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
 	asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// wait until the previous GPU has delivered rows [.., upto) of our left border (lane 0 spins, warp follows)
-constexpr unsigned kSpinLimit = 1u << 22;      // each spin costs an L2 round trip (~1 us): a dependency stuck for seconds is a bug
-// spin (lane 0) until the strip above has published `need` columns; the watchdog turns a protocol bug into an error
+// lexicographic "better" for best cells: higher score, then smaller i, then smaller j
+// (CPUBlockProcessor.cpp:154-158 row-major strict '<' + BestScoreList.hpp:30-38)
+__device__ __forceinline__ bool better(int s, int i, int j, int bs, int bi, int bj) {
+	return s > bs || (s == bs && (i < bi || (i == bi && j < bj)));
+}
+__device__ __forceinline__ unsigned long long global_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+// Spin-wait watchdog.  Waits in the strip chain are legitimately as long as a whole sweep of a column chunk on another
+// GPU, so the limit is a TIME without any observable progress (StripParams::watchdog_ns, sized by the engine from the
+// chunk width and the number of GPUs), not a spin count: a protocol bug becomes an error code, a slow neighbour does not.
+struct Watchdog {
+	unsigned long long t0;
+	unsigned spins;
+	int last;
+	__device__ __forceinline__ Watchdog() : t0(0), spins(0), last(INT_MIN) {}
+	// returns true when the wait must be abandoned (stop requested by another warp, or the deadline passed)
+	__device__ __forceinline__ bool expired(const StripParams& p, int observed, int code) {
+		if (ld_relaxed(p.stop_flag)) return true;
+		if ((++spins & 255u) == 0 && p.watchdog_ns > 0) {
+			const unsigned long long now = global_ns();
+			if (t0 == 0 || observed != last) { t0 = now; last = observed; }
+			else if (now - t0 > (unsigned long long)p.watchdog_ns) { atomicExch(p.stop_flag, code); return true; }
+		}
+		return false;
+	}
+};
+// spin (lane 0) until the strip above has published `need` columns
 __device__ __forceinline__ void wait_progress(const StripParams& p, int dep, int need, int lane) {
 	if (dep < 0) return;
 	if (lane == 0) {
-		unsigned spins = 0;
-		while (ld_acquire(p.progress + dep) < need) {
-			if (ld_relaxed(p.stop_flag)) break;
-			if (++spins > kSpinLimit) { atomicExch(p.stop_flag, 2); break; }
+		Watchdog wd;
+		int v;
+		while ((v = ld_acquire(p.progress + dep)) < need) {
+			if (wd.expired(p, v, 2)) break;
 			__nanosleep(64);
 		}
 	}
@@ -121,39 +206,127 @@ __device__ __forceinline__ void wait_progress(const StripParams& p, int dep, int
 __device__ __forceinline__ int wait_progress_v(const StripParams& p, int dep, int need, int lane) {
 	int v = 0;
 	if (lane == 0) {
-		unsigned spins = 0;
+		Watchdog wd;
 		while ((v = ld_acquire(p.progress + dep)) < need) {
-			if (ld_relaxed(p.stop_flag)) break;
-			if (++spins > kSpinLimit) { atomicExch(p.stop_flag, 2); break; }
+			if (wd.expired(p, v, 2)) break;
 			__nanosleep(64);
 		}
 	}
 	return __shfl_sync(0xffffffffu, v, 0);
 }
-__device__ __forceinline__ void wait_left(const StripParams& p, int upto, int lane) {
-	if (p.left_ready == nullptr) return;
+
+// ---- chain mode: work queue and readiness events -------------------------------------------------------------------
+__device__ __forceinline__ void chain_push(int* queue, int* tail, int job) {
+	__threadfence_system();
+	const int slot = atomicAdd_system(tail, 1);
+	st_release_sys(queue + slot, job);
+}
+// next job of this GPU in push order, or -1 when all of them have been handed out (or the kernel is stopping)
+__device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
+	int job = -1;
 	if (lane == 0) {
-		unsigned spins = 0;
-		while (ld_acquire_sys(p.left_ready) < upto) {
-			if (ld_relaxed(p.stop_flag)) break;
-			if (++spins > kSpinLimit) { atomicExch(p.stop_flag, 3); break; }
-			__nanosleep(256);
+		const int slot = atomicAdd(p.job_counter, 1);
+		if (slot < p.njobs) {
+			Watchdog wd;
+			while ((job = ld_acquire_sys(p.chain.queue + slot)) < 0) {
+				if (wd.expired(p, -1, 3)) { job = -1; break; }
+				__nanosleep(200);
+			}
 		}
 	}
-	__syncwarp();
+	return __shfl_sync(0xffffffffu, job, 0);
 }
-// publish our finished right-border rows to the next GPU; called before the strip's final progress release so
-// that publications of consecutive strips are ordered
-__device__ __forceinline__ void publish_right(const StripParams& p, int upto, int lane) {
-	if (p.right_ready == nullptr) return;
-	__syncwarp();
-	if (lane == 0) { __threadfence_system(); st_release_sys(p.right_ready, upto); }
+// top event: job (strip, k) has published its first columns, so (strip+1, k) may follow it (lane 0 only)
+// (out of line and fed with scalars only: a reference to the kernel parameters would force a local copy of them)
+__device__ __noinline__ void chain_notify_below_(unsigned long long* events, int* queue, int* tail, int nstrips, int job) {
+	const int k = job / nstrips, r = job - k * nstrips;
+	if (r + 1 >= nstrips) return;
+	const unsigned long long old = atomicAdd_system(events + r + 1, 1ULL);
+	if ((unsigned)(old & 0xffffffffu) == (unsigned)k && (unsigned)(old >> 32) >= (unsigned)k + 1u)
+		chain_push(queue, tail, job + 1);
+}
+__device__ __forceinline__ void chain_notify_below(const StripParams& p, int job) {
+	chain_notify_below_(p.chain.events, p.chain.queue, p.chain.q_tail, p.chain.nstrips, job);
+}
+// left event: job (strip, chunk c) has stored its right border into the next GPU's exchange block, so (strip, c+1) may
+// start over there (lane 0 only; the border stores of the other lanes are ordered by the __syncwarp of the caller)
+__device__ __noinline__ void chain_notify_right_(const ChunkCol* chunks, unsigned long long* nx_events, int* nx_queue, int* nx_tail,
+                                                 int nstrips, int nchunks_total, int world, int job) {
+	const int k = job / nstrips, r = job - k * nstrips;
+	const int gidx = chunks[k].gidx;
+	if (gidx + 1 >= nchunks_total) return;
+	const int kn = (gidx + 1) / world;                 // local index of chunk c+1 on its owner
+	__threadfence_system();
+	const unsigned long long old = atomicAdd_system(nx_events + r, 1ULL << 32);
+	if ((unsigned)(old >> 32) == (unsigned)kn && (unsigned)(old & 0xffffffffu) >= (unsigned)kn + 1u)
+		chain_push(nx_queue, nx_tail, kn * nstrips + r);
+}
+__device__ __forceinline__ void chain_notify_right(const StripParams& p, int job) {
+	chain_notify_right_(p.chain.chunks, p.chain.nx_events, p.chain.nx_queue, p.chain.nx_tail, p.chain.nstrips, p.chain.nchunks_total, p.chain.world, job);
+}
+
+// next job of this launch, or -1 (all lanes return the same value)
+__device__ __forceinline__ int claim_job(const StripParams& p, int lane) {
+	int job;
+	if (p.chain.enabled) job = chain_pop(p, lane);
+	else {
+		job = 0;
+		if (lane == 0) job = atomicAdd(p.job_counter, 1);
+		job = __shfl_sync(0xffffffffu, job, 0);
+		if (job >= p.njobs) job = -1;
+	}
+	if (job == 0 && p.test_delay_ms > 0) {
+		// test hook: everything chained behind the first strip must sit through this delay without tripping the watchdog
+		const unsigned long long t0 = global_ns();
+		while (global_ns() - t0 < (unsigned long long)p.test_delay_ms * 1000000ULL) __nanosleep(100000);
+	}
+	return job;
+}
+
+// Resolve job id -> JobCtx.  Outside chain mode the job table is explicit; in chain mode job = k * S + r and the
+// geometry comes from the strip and chunk tables.
+__device__ __forceinline__ JobCtx fetch_job(const StripParams& p, int job) {
+	JobCtx c;
+	c.job = job;
+	if (!p.chain.enabled) {
+		c.jb = p.jobs[job];
+		c.pidx = job; c.prog_base = 0;
+		return c;
+	}
+	const ChainParams& ch = p.chain;
+	const int k = job / ch.nstrips, r = job - k * ch.nstrips;
+	const StripRow sr = ch.strips[r];
+	const ChunkCol cc = ch.chunks[k];
+	c.jb.i0 = sr.i0; c.jb.rows = sr.rows; c.jb.j0 = cc.j0; c.jb.cols = cc.cols;
+	c.jb.dep = r - 1;
+	c.jb.flags = sr.flags;
+	c.jb.sra_off = sr.sra_row >= 0 ? (long long)sr.sra_row * ch.local_cols + cc.cum : -1;
+	c.jb.sra_index = (sr.sra_row >= 0 && k == ch.nchunks_local - 1) ? sr.sra_row : -1;   // the row is complete on this GPU after its last chunk
+	// borders inside the chain live in the exchange blocks, one private range of rows+1 slots per strip (offset
+	// left_off + r); the partition's own first / last column keep the layout of the single-GPU path
+	if (cc.gidx == 0) { c.jb.left_off = sr.left_off; if (ch.left_zero) c.jb.flags |= JOB_LEFT_ZERO; }
+	else { c.jb.left_off = sr.left_off + r; c.jb.flags |= JOB_LEFT_XCHG; }
+	if (cc.gidx == ch.nchunks_total - 1) c.jb.right_off = p.right ? sr.left_off : -1;
+	else { c.jb.right_off = sr.left_off + r; c.jb.flags |= JOB_RIGHT_PEER; }
+	c.pidx = r; c.prog_base = cc.cum;
+	return c;
+}
+// Chain mode keeps ONE result per strip: the jobs of a strip run strictly one after the other (chunk c+1 starts from
+// the border that chunk c delivers at its very end), so each job folds the strip's previous best into its own.
+__device__ __forceinline__ void store_result(const StripParams& p, const JobCtx& c, int bs, int bi, int bj) {
+	Score3 o; o.score = bs == INT_MIN ? -kInf : bs; o.i = bi; o.j = bj; o.pad = 0;
+	if (p.chain.enabled && c.job >= p.chain.nstrips) {
+		// written by another SM: read through L2 (the causality chain is (r,k-1) result -> fence -> left event -> ... -> our pop)
+		const int4 q = __ldcg(reinterpret_cast<const int4*>(p.results + c.pidx));
+		if (q.y >= 0 && (o.i < 0 || better(q.x, q.y, q.z, o.score, o.i, o.j))) { o.score = q.x; o.i = q.y; o.j = q.z; }
+	}
+	__stcg(reinterpret_cast<int4*>(p.results + c.pidx), make_int4(o.score, o.i, o.j, 0));
 }
 // tell the host that special row `jb.sra_index` is complete in the device-resident special-rows area, so that it can be
 // copied out and dispatched while the kernel keeps running (replaces the blocking per-block D2H of
 // R/src/CUDAligner.cpp:393-399)
 __device__ __forceinline__ void signal_special_row(const StripParams& p, const StripJob& jb, int lane) {
-	if (p.sra_done == nullptr || jb.sra_off < 0) return;
+	if (p.sra_done == nullptr || jb.sra_index < 0) return;
 	__syncwarp();
 	if (lane == 0) { __threadfence_system(); st_release_sys(p.sra_done + jb.sra_index, 1); }
 }
@@ -177,10 +350,5 @@ __device__ __forceinline__ void stcg_cell(Cell* p, int h, int x) {
 	__stcg(reinterpret_cast<int2*>(p), make_int2(h, x));
 }
 
-// lexicographic "better" for best cells: higher score, then smaller i, then smaller j
-// (CPUBlockProcessor.cpp:154-158 row-major strict '<' + BestScoreList.hpp:30-38)
-__device__ __forceinline__ bool better(int s, int i, int j, int bs, int bi, int bj) {
-	return s > bs || (s == bs && (i < bi || (i == bi && j < bj)));
-}
 
 }  // namespace b200

@@ -118,8 +118,9 @@ struct StripS16 {
 	// bound reaches the threshold (rows just below a high-scoring cell) is the exact maximum taken from the T registers,
 	// on the rare path.  The bound also feeds the pruning maximum, where an upper bound is all that is needed.
 	template <bool PARTIAL, bool CHECK, bool FILT = false>
-	__device__ __forceinline__ static void step(const StripParams& p, const StripJob& jb, State& s, Smem& sm, int warp, int lane,
+	__device__ __forceinline__ static void step(const StripParams& p, const JobCtx& cx, State& s, Smem& sm, int warp, int lane,
 	                                            int t, int u, int nv_lo, int nv_hi, int vo, int ro, int c0, int c1) {
+		const StripJob& jb = cx.jb;
 		const unsigned M2 = dup2(-kGapExt), M5 = dup2(-kGapFirst);
 		unsigned shH = __shfl_up_sync(0xffffffffu, s.botH, 1);
 		unsigned shF = __shfl_up_sync(0xffffffffu, s.botF, 1);
@@ -185,7 +186,7 @@ struct StripS16 {
 				s.blk = __vmaxs2(s.blk, smax);
 			}
 			if (CHECK && jb.right_off >= 0) {
-				Cell* rb = p.right + jb.right_off;
+				Cell* rb = right_border(p, cx);
 				if (col_lo == jb.cols - 1) {
 #pragma unroll
 					for (int r = 0; r < R; r++)
@@ -307,7 +308,8 @@ struct StripS16 {
 
 	template <bool PARTIAL>
 	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane, unsigned lut_addr = 0) {
-		const StripJob jb = p.jobs[job];
+		const JobCtx cx = fetch_job(p, job);
+		const StripJob& jb = cx.jb;
 		const int rows = jb.rows, cols = jb.cols, i0 = jb.i0, j0 = jb.j0;
 		const int rb_lo = (2 * lane) * R, rb_hi = (2 * lane + 1) * R;     // first row of each half inside the strip
 		int nv_lo = rows - rb_lo; nv_lo = nv_lo < 0 ? 0 : (nv_lo > R ? R : nv_lo);
@@ -321,10 +323,10 @@ struct StripS16 {
 		State s;
 		s.lut = lut_addr + 4u * (unsigned)lane;
 		asm volatile("mov.u32 %0, %0;" : "+r"(s.lut));          // opaque: keep it in a register instead of re-deriving it every step
-		if (!lz) wait_left(p, jb.left_off + rows, lane);
 		// ---- left border; the frame starts at the H of the corner
-		const Cell* lb = p.left + jb.left_off;
+		const Cell* lb = left_border(p, cx);
 		int base = 0;
+		int lmaxv = INT_MIN;                   // largest H of this lane's left-border cells (true scores)
 		if (!lz) {
 			int v0 = 0;
 			if (lane == 0) { v0 = __ldcg(&lb[0].h); if (v0 < -kInf / 2) v0 = __ldcg(&lb[1].h); if (v0 < -kInf / 2) v0 = 0; }
@@ -336,11 +338,11 @@ struct StripS16 {
 			int hl = -kGapFirst - base, el = kNeg, hh = -kGapFirst - base, eh = kNeg, cl = 0, chh = 0;
 			if (r < nv_lo) {
 				cl = code_of(p.s0[i0 + rb_lo + r]);
-				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_lo + r); hl = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); el = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
+				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_lo + r); lmaxv = max(lmaxv, c.h); hl = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); el = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
 			} else { hl = kNeg; }
 			if (r < nv_hi) {
 				chh = code_of(p.s0[i0 + rb_hi + r]);
-				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_hi + r); hh = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); eh = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
+				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_hi + r); lmaxv = max(lmaxv, c.h); hh = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); eh = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
 			} else { hh = kNeg; }
 			s.T[r] = pack2(clamp16(hl), clamp16(hh));
 			s.E[r] = pack2(el, eh);
@@ -362,10 +364,24 @@ struct StripS16 {
 		s.blk = 0x80008000u;
 
 		int flushed = 0;                       // columns of the bottom row published so far (computed or skipped)
-		int seen = jb.dep < 0 ? INT_MAX : 0;   // progress of the strip above observed by our last acquire (OPT_SEEN_CACHE)
+		int seen = jb.dep < 0 ? INT_MAX : 0;   // progress (in our columns) of the strip above observed by our last acquire (OPT_SEEN_CACHE)
 		const int opt = p.opt;
 		int pos = 0;                           // next column to decide in skip mode
-		bool computing = !(prune && lz);       // a zero left border lets the strip start in skip mode
+		const bool chained = p.chain.enabled != 0;   // chain mode: our first publication lets the strip below start
+		// A job that starts from a real left border (custom first column, or the border delivered by the chunk on our left
+		// in chain mode) must carry that border in the pruning test until every virtual lane has consumed its cells: the
+		// running block maxima only know the lanes that have started (the alignment path may enter through the lower rows).
+		int lpend = INT_MIN;
+		bool left_dead = false;
+		if (prune && !lz) {
+			lpend = __reduce_max_sync(0xffffffffu, lmaxv);
+			if (lpend < 0) lpend = 0;
+			const int g = ld_uniform(p.global_best);
+			if (g > s.thr) { s.thr = g; s.pub = g; s.thrp = thr_pack(s.thr, s.base); }
+			const int cols_left0 = p.prune_j1 - j0;
+			left_dead = s.thr != INT_MIN && (long long)lpend + kPruneSlack + (rows_left < cols_left0 ? rows_left : cols_left0) < (long long)s.thr;
+		}
+		bool computing = !(prune && (lz || left_dead));   // a zero (or dead) left border lets the strip start in skip mode
 		long long computed_cols = 0;
 		int bm1 = INT_MIN, bm2 = INT_MIN;      // maxima (true scores) of the last two computed 32-step blocks
 
@@ -374,8 +390,11 @@ struct StripS16 {
 				// =========================== SKIP mode: one 32-column block per iteration ===========================
 				if (pos >= cols) break;
 				const int need = pos + 32 < cols ? pos + 32 : cols;
-				if (!(opt & OPT_SEEN_CACHE)) wait_progress(p, jb.dep, need, lane);
-				else if (seen < need) seen = wait_progress_v(p, jb.dep, need, lane);
+				if (!(opt & OPT_SEEN_CACHE)) wait_progress(p, jb.dep, cx.prog_base + need, lane);
+				else if (seen < need) {
+					seen = wait_progress_v(p, jb.dep, cx.prog_base + need, lane) - cx.prog_base;
+					if (seen < need) return;           // the kernel is stopping (watchdog): do not sweep the rest of the strip
+				}
 				if (p.track == 2 && (!(opt & OPT_BEST_EVERY_4) || (pos & 96) == 0)) {
 					const int g = ld_uniform(p.global_best);
 					if (g > s.thr) { s.thr = g; s.pub = g; }
@@ -399,9 +418,14 @@ struct StripS16 {
 							stcg_cell(p.busH + j0 + pos + lane + 32 * k, 0, -kInf);
 							if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + pos + lane + 32 * k, 0, -kInf);
 						}
+						const bool first = chained && flushed == 0;
 						pos += 128; flushed = pos;
 						__syncwarp();
-						if (lane == 0) { if (!(opt & OPT_NO_SC_FENCE)) __threadfence(); st_release(p.progress + job, flushed); }
+						if (lane == 0) {
+							if (!(opt & OPT_NO_SC_FENCE)) __threadfence();
+							st_release(p.progress + cx.pidx, cx.prog_base + flushed);
+							if (first) chain_notify_below(p, job);
+						}
 						continue;
 					}
 				}
@@ -417,14 +441,20 @@ struct StripS16 {
 						stcg_cell(p.busH + j0 + c, 0, -kInf);
 						if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, 0, -kInf);
 					}
+					const bool first = chained && flushed == 0;
 					pos = need; flushed = need;
 					__syncwarp();
-					if (lane == 0) { if (!(opt & OPT_NO_SC_FENCE)) __threadfence(); st_release(p.progress + job, flushed); }
+					if (lane == 0) {
+						if (!(opt & OPT_NO_SC_FENCE)) __threadfence();
+						st_release(p.progress + cx.pidx, cx.prog_base + flushed);
+						if (first) chain_notify_below(p, job);
+					}
 					continue;
 				}
 				start_zero_segment(s, nv_lo, nv_hi, tmax);
 				computing = true;
 				bm1 = bm2 = INT_MIN;
+				lpend = INT_MIN;                   // the left neighbour of a restarted segment is the zero border
 			}
 
 			// =========================== COMPUTE mode: one segment [c0, c1) ===========================
@@ -454,8 +484,11 @@ struct StripS16 {
 				// ---- stage the next 32 columns of top border and seq1 (coalesced), gated on the strip above
 				if (tb < c1) {
 					const int need = tb + 32 < cols ? tb + 32 : cols;
-					if (!(opt & OPT_SEEN_CACHE)) wait_progress(p, jb.dep, need, lane);
-					else if (seen < need) seen = wait_progress_v(p, jb.dep, need, lane);
+					if (!(opt & OPT_SEEN_CACHE)) wait_progress(p, jb.dep, cx.prog_base + need, lane);
+					else if (seen < need) {
+						seen = wait_progress_v(p, jb.dep, cx.prog_base + need, lane) - cx.prog_base;
+						if (seen < need) return;       // the kernel is stopping (watchdog)
+					}
 					if (TRACK && p.track == 2 && (!(opt & OPT_BEST_EVERY_4) || (tb & 96) == 0 || tb == c0)) {
 						// share the running best: publish ours, adopt a higher one (monotone, staleness is harmless)
 						if (s.thr > s.pub) { if (lane == 0) push_best(p, s.thr); s.pub = s.thr; }
@@ -473,7 +506,13 @@ struct StripS16 {
 						in_max = in_max > bm2 ? in_max : bm2;
 						const int cols_left = p.prune_j1 - (j0 + tb);
 						const long long bound = (long long)in_max + kPruneSlack + (rows_left < cols_left ? rows_left : cols_left);
-						if (s.thr != INT_MIN && bm1 != INT_MIN && bound < (long long)s.thr) c1 = tb;
+						bool stop = s.thr != INT_MIN && bm1 != INT_MIN && bound < (long long)s.thr;
+						if (stop && lpend != INT_MIN && tb < c0 + 2 * V) {
+							// lanes that have not started yet still hold left-border cells: those enter at column c0
+							const int cl0 = p.prune_j1 - (j0 + c0);
+							stop = (long long)lpend + kPruneSlack + (rows_left < cl0 ? rows_left : cl0) < (long long)s.thr;
+						}
+						if (stop) c1 = tb;
 					}
 					if (tb < c1) {
 						int th = kNeg, tf = kNeg; unsigned pw = LUT ? 0u : 0x02020202u;
@@ -491,13 +530,13 @@ struct StripS16 {
 				const bool steady = (tb >= c0 + V) && (tb + 32 < c1);
 				if (steady && TRACK && s.thr >= kFiltMin) {
 #pragma unroll kStepUnroll
-					for (int u = 0; u < 32; u++) step<PARTIAL, false, true>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
+					for (int u = 0; u < 32; u++) step<PARTIAL, false, true>(p, cx, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
 				} else if (steady) {
 #pragma unroll kStepUnroll
-					for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
+					for (int u = 0; u < 32; u++) step<PARTIAL, false>(p, cx, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
 				} else {
 #pragma unroll 1
-					for (int u = 0; u < 32; u++) step<PARTIAL, true>(p, jb, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
+					for (int u = 0; u < 32; u++) step<PARTIAL, true>(p, cx, s, sm, warp, lane, tb + u, u, nv_lo, nv_hi, vo, ro, c0, c1);
 				}
 				if (TRACK) {
 					if (s.ncand > 0) drain(jb, s, sm, warp, lane, c0, c1);
@@ -526,24 +565,28 @@ struct StripS16 {
 					// released every 128 columns (a release costs a fence; the consumers run several blocks behind anyway)
 					const bool rel = !(opt & OPT_RELEASE_128) || cdone + 1 == cols || cdone < 2048 || tb + 32 >= c1 ||
 					                 ((cdone + 1) >> 7) != (flushed >> 7);
+					const bool first = chained && flushed == 0;      // (the first release is never deferred: cdone < 2048)
 					flushed = cdone + 1;
-					if (flushed == cols && jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
 					__syncwarp();
-					if (rel && lane == 0) { if (!(opt & OPT_NO_SC_FENCE)) __threadfence(); st_release(p.progress + job, flushed); }
+					if (rel && lane == 0) {
+						if (!(opt & OPT_NO_SC_FENCE)) __threadfence();
+						st_release(p.progress + cx.pidx, cx.prog_base + flushed);
+						if (first) chain_notify_below(p, job);
+					}
 				}
 			}
 			computed_cols += c1 - c0;
 			if (c1 >= cols) break;
 			pos = c1;                          // the segment was cut short: continue in skip mode
 			computing = false;
+			lpend = INT_MIN;
 		}
 
 		if (prune && !computing && jb.right_off >= 0) {
 			// the strip ended in skip mode: its right border is the zero border
-			Cell* rb = p.right + jb.right_off;
+			Cell* rb = right_border(p, cx);
 			for (int k = lane; k < rows; k += 32) stcg_cell(rb + 1 + k, 0, -kInf);
 			if (lane == 0) __stcg(&rb[0].h, 0);
-			publish_right(p, jb.left_off + rows, lane);
 		}
 
 		if (TRACK) {
@@ -556,10 +599,14 @@ struct StripS16 {
 				if (better(os, oi, oj, bs, bi, bj)) { bs = os; bi = oi; bj = oj; }
 			}
 			if (lane == 0) {
-				Score3 o; o.score = bs == INT_MIN ? -kInf : bs; o.i = bi; o.j = bj; o.pad = 0;
-				p.results[job] = o;
+				store_result(p, cx, bs, bi, bj);
 				if (bs != INT_MIN) push_best(p, bs);
 			}
+		}
+		if (p.chain.enabled) {
+			// the right border is in the next GPU's memory and our best is folded into the strip's result: hand the strip over
+			__syncwarp();
+			if (lane == 0) chain_notify_right(p, job);
 		}
 		signal_special_row(p, jb, lane);
 		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)computed_cols);
@@ -590,19 +637,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) strip_kernel_s16(const
 		lut_addr = (unsigned)__cvta_generic_to_shared(lut);
 	}
 	for (;;) {
-		int job = 0;
-		if (lane == 0) job = atomicAdd(p.job_counter, 1);
-		job = __shfl_sync(0xffffffffu, job, 0);
-		if (job >= p.njobs) break;
+		const int job = claim_job(p, lane);
+		if (job < 0) break;
 		if (ld_uniform(p.stop_flag)) break;
-		const int flags = p.jobs[job].flags, rows = p.jobs[job].rows;
+		int flags, rows;
+		if (p.chain.enabled) { const StripRow& sr = p.chain.strips[job % p.chain.nstrips]; flags = sr.flags; rows = sr.rows; }
+		else { flags = p.jobs[job].flags; rows = p.jobs[job].rows; }
 		if (flags & JOB_PRUNED) {
-			// same semantics as the int32 kernel: -INF to the right border, no score (CUDAligner.cu:950-960)
+			// diag path only. Same semantics as the int32 kernel: -INF to the right border, no score (CUDAligner.cu:950-960)
 			const StripJob jb = p.jobs[job];
 			if (jb.right_off >= 0)
 				for (int k = lane; k <= jb.rows; k += 32) stcg_cell(p.right + jb.right_off + k, -kInf, -kInf);
 			if (TRACK && lane == 0) { Score3 o; o.score = -kInf; o.i = -1; o.j = -1; o.pad = 0; p.results[job] = o; }
-			if (jb.right_off >= 0) publish_right(p, jb.left_off + jb.rows, lane);
 			__syncwarp();
 			if (lane == 0) { __threadfence(); st_release(p.progress + job, jb.cols); }
 			continue;

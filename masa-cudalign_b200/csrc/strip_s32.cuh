@@ -27,16 +27,16 @@ struct StripS32 {
 	};
 
 	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane) {
-		const StripJob jb = p.jobs[job];
+		const JobCtx cx = fetch_job(p, job);
+		const StripJob& jb = cx.jb;
 		const int rows = jb.rows, cols = jb.cols, i0 = jb.i0, j0 = jb.j0;
 
-		if (jb.flags & JOB_PRUNED) {
+		if (jb.flags & JOB_PRUNED) {             // diag path only (never in chain mode)
 			if (jb.right_off >= 0)
-				for (int k = lane; k <= rows; k += 32) stcg_cell(p.right + jb.right_off + k, -kInf, -kInf);
-			if (TRACK && lane == 0) { Score3 s; s.score = -kInf; s.i = -1; s.j = -1; s.pad = 0; p.results[job] = s; }
-			if (jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
+				for (int k = lane; k <= rows; k += 32) stcg_cell(right_border(p, cx) + k, -kInf, -kInf);
+			if (TRACK && lane == 0) { Score3 s; s.score = -kInf; s.i = -1; s.j = -1; s.pad = 0; p.results[cx.pidx] = s; }
 			__threadfence(); __syncwarp();
-			if (lane == 0) st_release(p.progress + job, cols);
+			if (lane == 0) st_release(p.progress + cx.pidx, cx.prog_base + cols);
 			return;
 		}
 
@@ -50,13 +50,12 @@ struct StripS32 {
 		for (int r = 0; r < R; r++) c0[r] = (r < nvalid) ? (int)p.s0[i0 + row_base + r] : 0x100;   // 0x100 never equals a byte
 
 		int tprev;   // H(row above this lane, previous column) - 5: diagonal term of row 0
-		if (!(jb.flags & JOB_LEFT_ZERO)) wait_left(p, jb.left_off + rows, lane);
 		if (jb.flags & JOB_LEFT_ZERO) {
 #pragma unroll
 			for (int r = 0; r < R; r++) { T[r] = 0 - kGapFirst; E[r] = -kInf; }
 			tprev = 0 - kGapFirst;
 		} else {
-			const Cell* lb = p.left + jb.left_off;
+			const Cell* lb = left_border(p, cx);
 #pragma unroll
 			for (int r = 0; r < R; r++) {
 				if (r < nvalid) { Cell c = ldcg_cell(lb + 1 + row_base + r); T[r] = c.h - kGapFirst; E[r] = c.x; }
@@ -77,7 +76,7 @@ struct StripS32 {
 			// ---- stage the next 32 columns of top border and seq1 (coalesced), gated on the strip above
 			if (tb < cols) {
 				int need = tb + 32 < cols ? tb + 32 : cols;
-				wait_progress(p, jb.dep, need, lane);
+				if (jb.dep >= 0 && wait_progress_v(p, jb.dep, cx.prog_base + need, lane) < cx.prog_base + need) return;   // stopping (watchdog)
 				int c = tb + lane;
 				Cell tv; tv.h = -kInf; tv.x = -kInf; unsigned char ch = 0;
 				if (c < cols) {
@@ -130,7 +129,7 @@ struct StripS32 {
 					if (lane == vo) { Cell o; o.h = oh; o.x = of; sm.bot[col & 63] = o; }
 					if (TRACK) trig = smax >= thr;
 					if (col == cols - 1 && jb.right_off >= 0) {
-						Cell* rb = p.right + jb.right_off;
+						Cell* rb = right_border(p, cx);
 #pragma unroll
 						for (int r = 0; r < R; r++)
 							if (r < nvalid) stcg_cell(rb + 1 + row_base + r, T[r] + kGapFirst, E[r]);
@@ -163,11 +162,14 @@ struct StripS32 {
 					stcg_cell(p.busH + j0 + c, v.h, v.x);
 					if (jb.sra_off >= 0) stcg_cell(p.sra + jb.sra_off + c, v.h, v.x);
 				}
+				const bool first = flushed == 0 && p.chain.enabled;      // chain mode: our first publication lets the strip below start
 				flushed = cdone + 1;
-				if (flushed == cols && jb.right_off >= 0) publish_right(p, jb.left_off + rows, lane);
 				__threadfence();
 				__syncwarp();
-				if (lane == 0) st_release(p.progress + job, flushed);
+				if (lane == 0) {
+					st_release(p.progress + cx.pidx, cx.prog_base + flushed);
+					if (first) chain_notify_below(p, job);
+				}
 			}
 		}
 
@@ -180,10 +182,14 @@ struct StripS32 {
 				if (better(os, oi, oj, bs, bi, bj)) { bs = os; bi = oi; bj = oj; }
 			}
 			if (lane == 0) {
-				Score3 s; s.score = bs == INT_MIN ? -kInf : bs; s.i = bi; s.j = bj; s.pad = 0;
-				p.results[job] = s;
+				store_result(p, cx, bs, bi, bj);
 				if (bs != INT_MIN) push_best(p, bs);
 			}
+		}
+		if (p.chain.enabled) {
+			// the right border is in the next GPU's memory and our result is folded into the strip's: hand the strip over
+			__syncwarp();
+			if (lane == 0) chain_notify_right(p, job);
 		}
 		signal_special_row(p, jb, lane);
 		if (lane == 0) atomicAdd(p.cells_done, (unsigned long long)rows * (unsigned long long)cols);
@@ -197,10 +203,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) strip_kernel_s32(const St
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	typename K::Smem& sm = smw[warp];
 	for (;;) {
-		int job = 0;
-		if (lane == 0) job = atomicAdd(p.job_counter, 1);
-		job = __shfl_sync(0xffffffffu, job, 0);
-		if (job >= p.njobs) break;
+		const int job = claim_job(p, lane);
+		if (job < 0) break;
 		if (ld_uniform(p.stop_flag)) break;
 		K::run_job(p, job, sm, warp, lane);
 	}

@@ -101,7 +101,7 @@ void B200Aligner::unsetSequences() {
 match_result_t B200Aligner::matchLastColumn(const cell_t* buffer, const cell_t* base, int len, int goalScore) {
 	/* The chunks are <= 1024 cells (C/common/AlignerManager.cpp:643-652): a device round trip would cost more
 	 * than the scan, so the host matcher of AbstractAligner is used; b200_match_last_column is the device
-	 * variant used when the column is already resident (tests/test_match_gpu.py). */
+	 * variant (parity: tests/test_match_gpu.py). */
 	return AbstractAligner::matchLastColumn(buffer, base, len, goalScore);
 }
 

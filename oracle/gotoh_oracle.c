@@ -11,7 +11,7 @@
  *   - pruning bound         C/libmasa/pruning/AbstractBlockPruning.cpp:70-113
  * Parity pinning: the reference ships no golden vectors; this file is pinned against
  * the reference's own code compiled from /root/reference (oracle/_ref/oracle_cpu, oracle_cpu_block) by
- * tests/test_oracle_pinning.py and the committed fixtures in tests/golden/.
+ * tests/test_oracle_cpu.py and the committed fixtures in tests/golden/.
  */
 #include "gotoh_oracle.h"
 #include <stdlib.h>
