@@ -7,10 +7,11 @@ driven by MASA-Core's own --fork (C/libmasa/libmasa.cpp:540-642), i.e. oracle/_r
 
     oracle_cpu_block --stage-1 --no-flush --fork=8 cfg1_A.fa cfg1_B.fa        (about 9 minutes on 8 cores)
 
---fork splits seq1 into 8 equal column slices (libmasa.cpp:632-635); every forked process writes the best cell of
-ITS slice to FORK.0k/crosspoints/crosspoint_01.00 (sw_stage1.cpp:480-491), 1-based.  The fixture keeps all eight,
-so the GPU tests can check the global best (the last slice's entry is not the best: the maximum over the slices is)
-and, through prefix partitions [0, j1_k), every intermediate one.  Needs oracle/_ref (build container only)."""
+--fork splits seq1 into 8 equal column slices (libmasa.cpp:632-635); every forked process writes one crosspoint to
+FORK.0k/crosspoints/crosspoint_01.00 (sw_stage1.cpp:480-491), 1-based: the LAST process the best cell of the whole
+matrix (the bests travel rightwards, sw_stage1.cpp:420-426), every other process the best cell on the LAST COLUMN of
+its slice (bestScoreLastColumn, AlignerManager.cpp:339-347; sw_stage1.cpp:230-236).  The fixture keeps all eight: the
+global best plus seven probes of single matrix columns.  Needs oracle/_ref (build container only)."""
 import hashlib
 import json
 import os
