@@ -350,7 +350,8 @@ def main():
 
     total = sum(step_times)
     e2e_total = sum(e2e_times)
-    my = dict(best=tuple(res["best"]), cells=int(res["cells"]), device_ms=sum(dev_ms) / max(len(dev_ms), 1))
+    my = dict(best=tuple(res["best"]), cells=int(res["cells"]), device_ms=sum(dev_ms) / max(len(dev_ms), 1),
+              warp_busy=res["warp_busy"], warps=res["warps"])
     if dist is not None:
         t = torch.tensor([total, e2e_total, sum(dev_ms) / 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -404,7 +405,8 @@ def main():
                    "cells_computed_frac": cells / float(m * n), "gcups_computed_cells": cells * K / total / 1e9,
                    "multi_gpu": None if world == 1 else {"scheme": "block-cyclic column chunks, P2P border stores + event-driven job queues in the strip kernel",
                                                           "chunks": res["chunks"], "chunk_cols": res["chunk_cols"]},
-                   "per_gpu": [{"cells_computed": p["cells"], "kernel_ms_per_step": p["device_ms"], "best": list(p["best"])} for p in per],
+                   "per_gpu": [{"cells_computed": p["cells"], "kernel_ms_per_step": p["device_ms"], "best": list(p["best"]),
+                                "warp_busy": p["warp_busy"], "resident_warps": p["warps"]} for p in per],
                    "per_gpu_cells_max_over_mean": max(p["cells"] for p in per) / mean_cells if mean_cells else None,
                    "published_other_hw": "README: 5Mx5M 48.98 GCUPS on GTX 560 Ti (all stages); 249Mx228M 82,822 GCUPS on 512xV100"},
         "device_ms_per_step": dev_total / K * 1e3,

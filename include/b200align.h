@@ -106,7 +106,8 @@ typedef struct {
 	int strips;                  /* strip jobs executed */
 	int kernel_launches;         /* kernels launched by this call */
 	int kernel_used;             /* B200_KERNEL_S32 | B200_KERNEL_S16X2 */
-	int reserved[5];             /* chained calls: [0] column chunks, [1] widest chunk */
+	int reserved[5];             /* [0] column chunks and [1] widest chunk of a chained call; [2] share of the resident warps'
+	                                time spent inside compute segments, per mille (packed kernel); [3] resident warps */
 } b200_result;
 
 typedef struct b200_handle b200_handle;

@@ -291,6 +291,8 @@ class Aligner:
         out["kernel_used"] = res.kernel_used
         out["chunks"] = res.reserved[0]
         out["chunk_cols"] = res.reserved[1]
+        out["warp_busy"] = res.reserved[2] / 1000.0
+        out["warps"] = res.reserved[3]
         out["rows"] = {i: np.concatenate(v) for i, v in out["rows"].items()}
         out["last_column"] = np.concatenate(out["last_column"]) if out["last_column"] else np.zeros(0, CELL)
         return out
@@ -313,7 +315,8 @@ class Aligner:
     def last_chain_result(self):
         r = Result()
         self._check(self.lib.b200_last_chain_result(self.h, C.byref(r)), "b200_last_chain_result")
-        return dict(best=(r.best.score, r.best.i, r.best.j), cells=r.cells, cells_total=r.cells_total, device_ms=r.device_ms)
+        return dict(best=(r.best.score, r.best.i, r.best.j), cells=r.cells, cells_total=r.cells_total, device_ms=r.device_ms,
+                    warp_busy=r.reserved[2] / 1000.0, warps=r.reserved[3])
 
     # ---- diag primitives -------------------------------------------------------------------------------
     def diag_begin(self, part: Partition, split, block_height):

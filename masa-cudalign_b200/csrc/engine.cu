@@ -137,6 +137,7 @@ struct b200_handle {
 	} s4;
 
 	Cell cont_corner;              // first-column cell of the last row of the previous chunk (B200_CONT_CHUNK)
+	int last_grid_warps = 0;
 	long long stat_cells = 0;
 	long long stat_launches = 0;
 };
@@ -277,6 +278,7 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 		else    fn = track ? (const void*)strip_kernel_s32<kR32, false, true> : (const void*)strip_kernel_s32<kR32, false, false>;
 	}
 	int grid = grid_for(h, fn, njobs, chained);
+	h->last_grid_warps = grid * kWarpsPerBlock;
 	void* args[] = {(void*)&sp};
 	CU(h, cudaLaunchKernel(fn, dim3(grid), dim3(kWarpsPerBlock * 32), args, 0, h->stream));
 	h->stat_launches++;
@@ -643,6 +645,12 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	out->cells_total = (long long)m * n;
 	out->cells = (long long)*reinterpret_cast<unsigned long long*>(h->hscalars.p + 4);
 	h->stat_cells += out->cells;
+	{
+		const double busy_ns = (double)*reinterpret_cast<unsigned long long*>(h->hscalars.p + 6);
+		const double cap_ns = (double)ms * 1e6 * h->last_grid_warps;
+		out->reserved[2] = cap_ns > 0 ? (int)(1000.0 * busy_ns / cap_ns) : 0;     // warp-time spent in compute segments, per mille
+		out->reserved[3] = h->last_grid_warps;
+	}
 
 	b200_score best; best.score = -kInf; best.i = -1; best.j = -1;
 	if (track) {
@@ -1284,6 +1292,13 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 		r.device_ms = ms; r.strips = S; r.kernel_launches = loc[q].njobs > 0 ? 1 : 0; r.kernel_used = kind;
 		r.cells = (long long)*reinterpret_cast<unsigned long long*>(h->hscalars.p + 4);
 		r.cells_total = (long long)m * loc[q].cols;
+		{
+			// share of the resident warps' time spent computing (per mille): the rest is waiting for a neighbour / the queue
+			const double busy_ns = (double)*reinterpret_cast<unsigned long long*>(h->hscalars.p + 6);
+			const double cap_ns = (double)ms * 1e6 * h->last_grid_warps;
+			r.reserved[2] = cap_ns > 0 ? (int)(1000.0 * busy_ns / cap_ns) : 0;
+			r.reserved[3] = h->last_grid_warps;
+		}
 		r.best.score = -kInf; r.best.i = r.best.j = -1;
 		if (track)
 			for (int k = 0; k < S; k++) {
@@ -1307,6 +1322,11 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 	if (stop != 0) { h0->err = "strip kernel watchdog: a border dependency did not advance (code " + std::to_string(stop) + ")"; return 5; }
 	out->strips = S; out->kernel_used = kind; out->cells_total = (long long)m * n; out->best = best;
 	out->reserved[0] = C; out->reserved[1] = chunk_max;
+	{
+		long long busy = 0, warps = 0;
+		for (int q = 0; q < nlocal; q++) { busy += (long long)hs[q]->last_chain.reserved[2] * hs[q]->last_chain.reserved[3]; warps += hs[q]->last_chain.reserved[3]; }
+		out->reserved[2] = warps ? (int)(busy / warps) : 0; out->reserved[3] = (int)warps;
+	}
 
 	// ---- remaining artefacts
 	if (have_cb) {

@@ -100,7 +100,7 @@ struct StripParams {
 	int* progress;          // [njobs] columns of the bottom row published so far
 	Score3* results;        // [njobs] best cell of each job (track != 0)
 	int* global_best;       // running best score of the whole partition (atomicMax)
-	unsigned long long* cells_done;   // statistics
+	unsigned long long* cells_done;   // statistics: [0] cells computed, [1] nanoseconds spent by warps inside compute segments
 	int* stop_flag;         // non-zero asks the kernel to stop (set by a spin-wait watchdog: no hung GPU on a protocol bug)
 	int* peer_best[8];      // multi-GPU: running-best words of the other GPUs (peer memory)
 	int n_peer_best;
