@@ -77,7 +77,8 @@ struct b200_handle {
 	DevBuf<StripJob> jobs;
 	DevBuf<int> progress;
 	DevBuf<Score3> results;
-	DevBuf<int> scalars;            // [0] job counter, [1] global best, [2] stop flag, [4..5] cells (u64)
+	DevBuf<int> scalars;            // [0] job counter, [1] global best, [2] stop flag, [4..5] cells (u64), [6..7] busy ns (u64)
+	DevBuf<int> smload;             // chain mode: computing warps of the GPU [0] and per SM [1 + smid]
 	DevBuf<Cell> matchbuf;          // scratch of b200_match_last_column (its own: the call may come between chunked launches)
 	DevBuf<int> matchflag;
 	PinBuf<int> hmatchflag;
@@ -246,6 +247,12 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.left = h->ov.left ? h->ov.left : h->left.p;
 	sp.right = h->ov.no_right ? nullptr : (h->ov.right ? h->ov.right : h->right.p);
 	sp.chain = h->ov.chain;
+	sp.sm_load = nullptr; sp.nsm = h->sm_count;
+	if (sp.chain.enabled && !getenv("B200_NO_SM_BALANCE")) {
+		CU(h, h->smload.reserve(512));
+		CU(h, cudaMemsetAsync(h->smload.p, 0, 512 * sizeof(int), h->stream));
+		sp.sm_load = h->smload.p;
+	}
 	sp.watchdog_ns = watchdog_ns(h);
 	{ const char* e = getenv("B200_TEST_DELAY_MS"); sp.test_delay_ms = e ? atoi(e) : 0; }
 	sp.n_peer_best = h->ov.npeer;
@@ -357,7 +364,7 @@ extern "C" void b200_destroy(b200_handle* h) {
 	h->s0.release(); h->s1.release(); h->busH.release(); h->left.release(); h->right.release(); h->sra.release();
 	h->jobs.release(); h->progress.release(); h->results.release(); h->scalars.release();
 	h->hcells.release(); h->hresults.release(); h->hscalars.release();
-	h->matchbuf.release(); h->matchflag.release(); h->hmatchflag.release();
+	h->matchbuf.release(); h->matchflag.release(); h->hmatchflag.release(); h->smload.release();
 	h->dg.vbuf.release(); h->dg.col0.release(); h->dg.hlastcol.release();
 	h->s4.s0r.release(); h->s4.s1r.release(); h->s4.left.release(); h->s4.halves.release(); h->s4.parts.release(); h->s4.out.release();
 	for (int k = 0; k < 4; k++) h->s4.bus[k].release();

@@ -111,6 +111,8 @@ struct StripParams {
 	int prune_i1, prune_j1; // end of the (super) partition: bounds of the distance term of the pruning test
 	int opt;                // StripOpt bits: protocol variants of the strip chain (engine default, B200_OPT overrides)
 	long long watchdog_ns;  // a dependency that shows no progress for this long stops the kernel with an error (0 = never)
+	int* sm_load;           // chain mode: [0] warps inside compute segments on this GPU, [1 + smid] the same per SM (job placement)
+	int nsm;                // SMs of this GPU
 	int test_delay_ms;      // test hook: the first job sleeps this long before it starts (tests/test_watchdog_gpu.py)
 	ChainParams chain;
 };
@@ -221,17 +223,39 @@ __device__ __forceinline__ void chain_push(int* queue, int* tail, int job) {
 	const int slot = atomicAdd_system(tail, 1);
 	st_release_sys(queue + slot, job);
 }
-// next job of this GPU in push order, or -1 when all of them have been handed out (or the kernel is stopping)
+__device__ __forceinline__ unsigned sm_id() {
+	unsigned v;
+	asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+	return v;
+}
+// Next job of this GPU in push order, or -1 when all of them have been handed out (or the kernel is stopping).
+// A job is taken only once it is actually in the queue, and preferably by a warp whose SM carries no more computing
+// warps than the average SM: the strips of a wavefront advance in lockstep (each one waits for the strip above), so the
+// whole front moves at the pace of the most crowded SM -- with the GPU half empty (multi-GPU runs, narrow pruning
+// bands) random placement costs far more than the few microseconds an idle warp waits for a better-placed taker.
 __device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
 	int job = -1;
 	if (lane == 0) {
-		const int slot = atomicAdd(p.job_counter, 1);
-		if (slot < p.njobs) {
-			Watchdog wd;
-			while ((job = ld_acquire_sys(p.chain.queue + slot)) < 0) {
-				if (wd.expired(p, -1, 3)) { job = -1; break; }
-				__nanosleep(200);
+		Watchdog wd;
+		const unsigned smid = sm_id();
+		int refused = 0;
+		for (;;) {
+			const int head = ld_relaxed(p.job_counter);
+			if (head >= p.njobs) break;
+			const int tail = ld_acquire_sys(p.chain.q_tail);
+			if (head < tail) {
+				bool take = true;
+				if (p.sm_load != nullptr && refused < 8)
+					take = (long long)ld_relaxed(p.sm_load + 1 + smid) * p.nsm <= (long long)ld_relaxed(p.sm_load);
+				if (!take) { refused++; __nanosleep(1000); continue; }
+				if (atomicCAS(p.job_counter, head, head + 1) != head) continue;          // another warp took it
+				while ((job = ld_acquire_sys(p.chain.queue + head)) < 0) {                // the tail moves before the entry is stored
+					if (wd.expired(p, -1, 3)) { job = -1; break; }
+				}
+				break;
 			}
+			if (wd.expired(p, tail, 3)) break;
+			__nanosleep(2000);
 		}
 	}
 	return __shfl_sync(0xffffffffu, job, 0);

@@ -461,6 +461,7 @@ struct StripS16 {
 			const int c0 = pos;
 			int c1 = cols;
 			const unsigned long long seg_t0 = global_ns();     // statistics: time this warp spends in compute segments
+			if (chained && p.sm_load != nullptr && lane == 0) { atomicAdd(p.sm_load, 1); atomicAdd(p.sm_load + 1 + sm_id(), 1); }
 #pragma unroll 1
 			for (int tb = c0; tb < c1 + V - 1; tb += 32) {
 				// ---- re-centre the frame on H(row 0 of the strip, last column done by virtual lane 0)
@@ -577,7 +578,10 @@ struct StripS16 {
 				}
 			}
 			computed_cols += c1 - c0;
-			if (lane == 0) atomicAdd(p.cells_done + 1, global_ns() - seg_t0);
+			if (lane == 0) {
+				atomicAdd(p.cells_done + 1, global_ns() - seg_t0);
+				if (chained && p.sm_load != nullptr) { atomicSub(p.sm_load, 1); atomicSub(p.sm_load + 1 + sm_id(), 1); }
+			}
 			if (c1 >= cols) break;
 			pos = c1;                          // the segment was cut short: continue in skip mode
 			computing = false;

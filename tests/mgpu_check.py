@@ -92,7 +92,7 @@ def main():
                 if arte:
                     good &= ids == list(range(8192, m, 8192))
                     for i in ids + [m]:
-                        row = assemble([g["rows"][i] for g in got], chunks)
+                        row = assemble([g["rows"].get(i, np.zeros(0, O.CELL)) for g in got], chunks)     # a rank may own no chunk
                         good &= np.array_equal(row, o["rows"][i - 1])
                     good &= np.array_equal(got[last_owner]["last_column"], o["last_col"])
                 ref = "oracle"
