@@ -249,8 +249,8 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.chain = h->ov.chain;
 	sp.sm_load = nullptr; sp.nsm = h->sm_count;
 	if (sp.chain.enabled && !getenv("B200_NO_SM_BALANCE")) {
-		CU(h, h->smload.reserve(512));
-		CU(h, cudaMemsetAsync(h->smload.p, 0, 512 * sizeof(int), h->stream));
+		CU(h, h->smload.reserve(1024));
+		CU(h, cudaMemsetAsync(h->smload.p, 0, 1024 * sizeof(int), h->stream));
 		sp.sm_load = h->smload.p;
 	}
 	sp.watchdog_ns = watchdog_ns(h);
@@ -442,7 +442,7 @@ extern "C" int b200_special_row_ids(int height, int block_height, int interval, 
 // Strips of a partition: cut every kSH16F (packed) / kSH32 (int32) rows and additionally at the reference's special-row
 // ids, so that every special row is the bottom row of a strip.  Identical on every GPU of a chain.
 static void build_strips(b200_handle* h, const b200_partition* p, int m, const std::vector<int>& sr_ids,
-                         std::vector<StripRow>& rows, bool& any_s16) {
+                         std::vector<StripRow>& rows, bool& any_s16, int sh16 = kSH16F) {
 	rows.clear();
 	any_s16 = false;
 	// rows [a, b) of the partition free of non-ACGT bytes?  (64-row granularity, conservative)
@@ -464,7 +464,7 @@ static void build_strips(b200_handle* h, const b200_partition* p, int m, const s
 		if (allow16 && rows_clean(r, std::min(lim, r + kSH32))) {
 			s16 = true;
 			end = std::min(lim, r + kSH32);
-			if (end == r + kSH32 && end < lim && rows_clean(end, std::min(lim, r + kSH16F))) end = std::min(lim, r + kSH16F);
+			if (sh16 > kSH32 && end == r + kSH32 && end < lim && rows_clean(end, std::min(lim, r + sh16))) end = std::min(lim, r + sh16);
 		} else {
 			s16 = false;
 			end = std::min(lim, r + kSH32);
@@ -1078,9 +1078,16 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 	int bh = p->block_height > 0 ? p->block_height : 4 * std::min(128, n);
 	std::vector<int> sr_ids;
 	if (p->want_special_rows) special_row_ids(m, bh, p->special_row_interval, sr_ids);
+	// Strip height of the packed kernel: 1024 rows (16 per virtual lane) is the cheapest per cell, but a front needs about
+	// 2400 resident strips per GPU to fill it; when the rows cannot provide that many per GPU, 512-row strips (8 per
+	// virtual lane) double the number of strips and halve the dependent chain of a step.  B200_CHAIN_SH overrides.
+	int sh16 = kSH16F;
+	if (h0->acgt_only && (long long)m / kSH16F < 1600LL * world) sh16 = kSH16;
+	if (const char* e = getenv("B200_CHAIN_SH")) sh16 = atoi(e) == kSH16 ? kSH16 : kSH16F;
+	if (!h0->acgt_only) sh16 = kSH16F;
 	std::vector<StripRow> srows;
 	bool any_s16 = false;
-	build_strips(h0, p, m, sr_ids, srows, any_s16);
+	build_strips(h0, p, m, sr_ids, srows, any_s16, sh16);
 	const int S = (int)srows.size();
 	const int kind = any_s16 ? B200_KERNEL_S16X2 : B200_KERNEL_S32;
 	std::vector<int> bounds;
@@ -1219,7 +1226,7 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 		if (dbg) fprintf(stderr, "[b200] chain rank %d/%d: %d strips x %d chunks (of %d, <= %d columns), prune=%d kind=%d\n", h->mg.rank, world, S, (int)L.chunks.size(), C, chunk_max, h->ov.prune, kind);
 		int lrc = 0;
 		CU(h, cudaEventRecord(h->ev0, h->stream));
-		if (L.njobs > 0) lrc = launch_strips(h, (int)L.njobs, p->recurrence, track, kind, kSH16F, true);
+		if (L.njobs > 0) lrc = launch_strips(h, (int)L.njobs, p->recurrence, track, kind, sh16, true);
 		CU(h, cudaEventRecord(h->ev1, h->stream));
 		memset(&ch, 0, sizeof(ch));
 		h->ov.gbest = nullptr; h->ov.npeer = 0; h->ov.prune = 0; h->ov.sra_done = nullptr; h->ov.mixed = false; h->ov.no_right = false; h->ov.chunk_cols_max = 0;
@@ -1328,7 +1335,7 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 	}
 	if (stop != 0) { h0->err = "strip kernel watchdog: a border dependency did not advance (code " + std::to_string(stop) + ")"; return 5; }
 	out->strips = S; out->kernel_used = kind; out->cells_total = (long long)m * n; out->best = best;
-	out->reserved[0] = C; out->reserved[1] = chunk_max;
+	out->reserved[0] = C; out->reserved[1] = chunk_max; out->reserved[4] = sh16;
 	{
 		long long busy = 0, warps = 0;
 		for (int q = 0; q < nlocal; q++) { busy += (long long)hs[q]->last_chain.reserved[2] * hs[q]->last_chain.reserved[3]; warps += hs[q]->last_chain.reserved[3]; }

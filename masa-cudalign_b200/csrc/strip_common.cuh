@@ -111,7 +111,7 @@ struct StripParams {
 	int prune_i1, prune_j1; // end of the (super) partition: bounds of the distance term of the pruning test
 	int opt;                // StripOpt bits: protocol variants of the strip chain (engine default, B200_OPT overrides)
 	long long watchdog_ns;  // a dependency that shows no progress for this long stops the kernel with an error (0 = never)
-	int* sm_load;           // chain mode: [0] warps inside compute segments on this GPU, [1 + smid] the same per SM (job placement)
+	int* sm_load;           // chain mode: [0] warps inside compute segments on this GPU, [1 + 4 * smid + scheduler] the same per warp scheduler
 	int nsm;                // SMs of this GPU
 	int test_delay_ms;      // test hook: the first job sleeps this long before it starts (tests/test_watchdog_gpu.py)
 	ChainParams chain;
@@ -228,16 +228,19 @@ __device__ __forceinline__ unsigned sm_id() {
 	asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
 	return v;
 }
+// index of this warp's scheduler in StripParams::sm_load (a CTA's four warps sit on the four sub-partitions of its SM)
+__device__ __forceinline__ unsigned sched_slot() { return 4u * sm_id() + ((threadIdx.x >> 5) & 3u); }
 // Next job of this GPU in push order, or -1 when all of them have been handed out (or the kernel is stopping).
-// A job is taken only once it is actually in the queue, and preferably by a warp whose SM carries no more computing
-// warps than the average SM: the strips of a wavefront advance in lockstep (each one waits for the strip above), so the
-// whole front moves at the pace of the most crowded SM -- with the GPU half empty (multi-GPU runs, narrow pruning
-// bands) random placement costs far more than the few microseconds an idle warp waits for a better-placed taker.
+// A job is taken only once it is actually in the queue, and preferably by a warp whose scheduler (SM sub-partition)
+// carries no more computing warps than the average one: the strips of a wavefront advance in lockstep (each one waits
+// for the strip above), so the whole front moves at the pace of the most crowded scheduler -- with the GPU half empty
+// (multi-GPU runs, narrow pruning bands) random placement costs far more than the few microseconds an idle warp waits
+// for a better-placed taker.
 __device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
 	int job = -1;
 	if (lane == 0) {
 		Watchdog wd;
-		const unsigned smid = sm_id();
+		const unsigned slot_id = sched_slot();
 		int refused = 0;
 		for (;;) {
 			const int head = ld_relaxed(p.job_counter);
@@ -246,7 +249,7 @@ __device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
 			if (head < tail) {
 				bool take = true;
 				if (p.sm_load != nullptr && refused < 8)
-					take = (long long)ld_relaxed(p.sm_load + 1 + smid) * p.nsm <= (long long)ld_relaxed(p.sm_load);
+					take = (long long)ld_relaxed(p.sm_load + 1 + slot_id) * (4 * p.nsm) <= (long long)ld_relaxed(p.sm_load);
 				if (!take) { refused++; __nanosleep(1000); continue; }
 				if (atomicCAS(p.job_counter, head, head + 1) != head) continue;          // another warp took it
 				while ((job = ld_acquire_sys(p.chain.queue + head)) < 0) {                // the tail moves before the entry is stored

@@ -461,7 +461,7 @@ struct StripS16 {
 			const int c0 = pos;
 			int c1 = cols;
 			const unsigned long long seg_t0 = global_ns();     // statistics: time this warp spends in compute segments
-			if (chained && p.sm_load != nullptr && lane == 0) { atomicAdd(p.sm_load, 1); atomicAdd(p.sm_load + 1 + sm_id(), 1); }
+			if (chained && p.sm_load != nullptr && lane == 0) { atomicAdd(p.sm_load, 1); atomicAdd(p.sm_load + 1 + sched_slot(), 1); }
 #pragma unroll 1
 			for (int tb = c0; tb < c1 + V - 1; tb += 32) {
 				// ---- re-centre the frame on H(row 0 of the strip, last column done by virtual lane 0)
@@ -580,7 +580,7 @@ struct StripS16 {
 			computed_cols += c1 - c0;
 			if (lane == 0) {
 				atomicAdd(p.cells_done + 1, global_ns() - seg_t0);
-				if (chained && p.sm_load != nullptr) { atomicSub(p.sm_load, 1); atomicSub(p.sm_load + 1 + sm_id(), 1); }
+				if (chained && p.sm_load != nullptr) { atomicSub(p.sm_load, 1); atomicSub(p.sm_load + 1 + sched_slot(), 1); }
 			}
 			if (c1 >= cols) break;
 			pos = c1;                          // the segment was cut short: continue in skip mode
@@ -623,7 +623,7 @@ struct StripS16 {
 // variant plus the int32 path.  Pure A/C/G/T launches of the whole-partition instance (R = kR16F) use the LUT variant.
 template <int R, bool SW, bool TRACK, bool MIXED = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) strip_kernel_s16(const StripParams p) {
-	constexpr bool LUT = !MIXED && R == kR16F;
+	constexpr bool LUT = !MIXED;
 	using K = StripS16<R, SW, TRACK, LUT>;
 	using K32 = StripS32<16, SW, TRACK>;
 	__shared__ union { typename K::Smem s16; typename K32::Smem s32; } smu[kWarpsPerBlock];   // per warp: warps run different job kinds
