@@ -248,7 +248,9 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.right = h->ov.no_right ? nullptr : (h->ov.right ? h->ov.right : h->right.p);
 	sp.chain = h->ov.chain;
 	sp.sm_load = nullptr; sp.nsm = h->sm_count;
-	if (sp.chain.enabled && !getenv("B200_NO_SM_BALANCE")) {
+	// scheduler-balanced job placement (strip_common.cuh chain_pop): implemented, measured, and OFF by default -- on an
+	// under-filled GPU it was 10 % slower than first-come placement (profiles/r02_chain_starvation.txt)
+	if (sp.chain.enabled && getenv("B200_SM_BALANCE")) {
 		CU(h, h->smload.reserve(1024));
 		CU(h, cudaMemsetAsync(h->smload.p, 0, 1024 * sizeof(int), h->stream));
 		sp.sm_load = h->smload.p;
@@ -258,7 +260,7 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.n_peer_best = h->ov.npeer;
 	for (int k = 0; k < 8; k++) sp.peer_best[k] = k < h->ov.npeer ? h->ov.peer_best[k] : nullptr;
 	sp.jobs = h->jobs.p + h->ov.job_off; sp.njobs = njobs;
-	sp.job_counter = h->ov.counter ? h->ov.counter : h->scalars.p + 0;
+	sp.job_counter = h->ov.counter ? h->ov.counter : h->scalars.p + (h->ov.chain.enabled ? 32 : 0);   // chain: polled by idle warps, own 128-byte line
 	sp.global_best = h->ov.gbest ? h->ov.gbest : h->scalars.p + 1;
 	sp.stop_flag = h->scalars.p + 2;
 	sp.cells_done = reinterpret_cast<unsigned long long*>(h->scalars.p + 4);
@@ -293,11 +295,12 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 }
 
 int reset_scalars(b200_handle* h, int global_best) {
-	CU(h, h->scalars.reserve(16));
-	CU(h, h->hscalars.reserve(16));
+	CU(h, h->scalars.reserve(64));
+	CU(h, h->hscalars.reserve(64));
 	int* s = h->hscalars.p;
-	s[0] = 0; s[1] = global_best; s[2] = 0; s[3] = 0; s[4] = 0; s[5] = 0; s[6] = 0; s[7] = 0;
-	CU(h, cudaMemcpyAsync(h->scalars.p, s, 8 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+	memset(s, 0, 64 * sizeof(int));
+	s[1] = global_best;
+	CU(h, cudaMemcpyAsync(h->scalars.p, s, 64 * sizeof(int), cudaMemcpyHostToDevice, h->stream));
 	return 0;
 }
 
@@ -923,8 +926,8 @@ namespace {
 
 // Exchange block of one GPU (peer-visible): [64 control ints][events u64 x cap_strips][queue int x cap_jobs][cells].
 //   ctrl[1], ctrl[2]  running best score shared by all GPUs; chained call e uses word 1 + (e & 1)
-//   ctrl[8]           queue tail (jobs pushed so far)
-constexpr int kCtlBest = 1, kCtlTail = 8, kCtlInts = 64;
+//   ctrl[32]          queue tail (jobs pushed so far)
+constexpr int kCtlBest = 1, kCtlTail = 32, kCtlInts = 64;      // the tail is polled by every idle warp: its own 128-byte line
 struct ExLayout { size_t off_events, off_queue, off_cells, bytes; };
 ExLayout ex_layout(long long cap_rows, long long cap_strips, long long cap_jobs) {
 	ExLayout l;

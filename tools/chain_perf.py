@@ -25,6 +25,7 @@ ap.add_argument("--prune", action="store_true")
 ap.add_argument("--chunk", type=int, default=65536)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--modes", default="single,chain")
+ap.add_argument("--warps-per-sm", type=int, default=0)
 args = ap.parse_args()
 if args.config:
     a, b = synth.make_config(args.config, args.scale)
@@ -34,7 +35,7 @@ else:
 m, n = a.size, b.size
 out = {"m": m, "n": n, "prune": args.prune, "chunk": args.chunk}
 for mode in args.modes.split(","):
-    al = b200.Aligner()
+    al = b200.Aligner(warps_per_sm=args.warps_per_sm)
     if mode == "chain":
         al.mgpu_setup(None, 0, 1, m, n, args.chunk)
     al.set_sequences(a, b)
