@@ -126,6 +126,7 @@ struct b200_handle {
 		const unsigned char* s0 = nullptr; const unsigned char* s1 = nullptr; Cell* busH = nullptr;
 		int job_off = 0; int* counter = nullptr;
 		long long chunk_cols_max = 0;
+		unsigned long long* trace = nullptr; unsigned long long* nx_trace = nullptr;
 		int* sra_done = nullptr;
 		bool mixed = false;
 	} ov;
@@ -248,6 +249,7 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.right = h->ov.no_right ? nullptr : (h->ov.right ? h->ov.right : h->right.p);
 	sp.chain = h->ov.chain;
 	sp.sm_load = nullptr; sp.nsm = h->sm_count;
+	sp.trace = h->ov.trace; sp.nx_trace = h->ov.nx_trace;
 	// scheduler-balanced job placement (strip_common.cuh chain_pop): implemented, measured, and OFF by default -- on an
 	// under-filled GPU it was 10 % slower than first-come placement (profiles/r02_chain_starvation.txt)
 	if (sp.chain.enabled && getenv("B200_SM_BALANCE")) {
@@ -928,13 +930,15 @@ namespace {
 //   ctrl[1], ctrl[2]  running best score shared by all GPUs; chained call e uses word 1 + (e & 1)
 //   ctrl[32]          queue tail (jobs pushed so far)
 constexpr int kCtlBest = 1, kCtlTail = 32, kCtlInts = 64;      // the tail is polled by every idle warp: its own 128-byte line
-struct ExLayout { size_t off_events, off_queue, off_cells, bytes; };
+struct ExLayout { size_t off_events, off_queue, off_cells, off_trace, bytes; };
+bool trace_enabled() { return getenv("B200_TRACE_DIR") != nullptr; }       // development: per-job timestamps (tools/trace_report.py)
 ExLayout ex_layout(long long cap_rows, long long cap_strips, long long cap_jobs) {
 	ExLayout l;
 	l.off_events = kCtlInts * sizeof(int);
 	l.off_queue = l.off_events + (size_t)cap_strips * sizeof(unsigned long long);
 	l.off_cells = (l.off_queue + (size_t)cap_jobs * sizeof(int) + 15) & ~(size_t)15;
-	l.bytes = l.off_cells + ((size_t)cap_rows + (size_t)cap_strips + 8) * sizeof(Cell);
+	l.off_trace = l.off_cells + ((size_t)cap_rows + (size_t)cap_strips + 8) * sizeof(Cell);
+	l.bytes = l.off_trace + (trace_enabled() ? (size_t)cap_jobs * 32 : 0);
 	return l;
 }
 long long strips_cap_for(long long max_rows) { return max_rows / 256 + 4096; }
@@ -962,6 +966,7 @@ int alloc_exchange(b200_handle* h, long long max_rows, long long max_jobs) {
 	const ExLayout l = ex_layout(h->mg.cap_rows, h->mg.cap_strips, h->mg.cap_jobs);
 	CU(h, cudaMalloc((void**)&h->mg.block, l.bytes));
 	CU(h, cudaMemset(h->mg.block, 0, l.off_cells));
+	if (trace_enabled()) CU(h, cudaMemset(reinterpret_cast<char*>(h->mg.block) + l.off_trace, 0, l.bytes - l.off_trace));
 	return 0;
 }
 
@@ -1215,6 +1220,8 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 		ch.nx_queue = reinterpret_cast<int*>(next + l.off_queue); ch.nx_tail = h->mg.peers[nxr] + kCtlTail;
 		ch.nx_events = reinterpret_cast<unsigned long long*>(next + l.off_events);
 		ch.nx_cells = reinterpret_cast<Cell*>(next + l.off_cells);
+		h->ov.trace = trace_enabled() ? reinterpret_cast<unsigned long long*>(mine + l.off_trace) : nullptr;
+		h->ov.nx_trace = trace_enabled() ? reinterpret_cast<unsigned long long*>(next + l.off_trace) : nullptr;
 		const int word = kCtlBest + (int)(h->mg.epoch & 1u);
 		h->ov.gbest = h->mg.block + word;
 		h->ov.npeer = 0;
@@ -1232,6 +1239,7 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 		if (L.njobs > 0) lrc = launch_strips(h, (int)L.njobs, p->recurrence, track, kind, sh16, true);
 		CU(h, cudaEventRecord(h->ev1, h->stream));
 		memset(&ch, 0, sizeof(ch));
+		h->ov.trace = nullptr; h->ov.nx_trace = nullptr;
 		h->ov.gbest = nullptr; h->ov.npeer = 0; h->ov.prune = 0; h->ov.sra_done = nullptr; h->ov.mixed = false; h->ov.no_right = false; h->ov.chunk_cols_max = 0;
 		if (lrc) { h0->err = h->err; return 1; }
 	}
@@ -1329,6 +1337,17 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 		out->device_ms = std::max(out->device_ms, (double)ms);
 		out->kernel_launches += r.kernel_launches;
 		if (r.best.i >= 0 && (r.best.score > best.score || (r.best.score == best.score && (r.best.i < best.i || (r.best.i == best.i && r.best.j < best.j))))) best = r.best;
+		if (trace_enabled()) {
+			// development: dump {pushed, popped, first publication, finished} of every job of this GPU (last call wins)
+			const ExLayout l = ex_layout(h->mg.cap_rows, h->mg.cap_strips, h->mg.cap_jobs);
+			std::vector<unsigned long long> tr((size_t)loc[q].njobs * 4 + 8);
+			tr[0] = (unsigned long long)S; tr[1] = loc[q].chunks.size(); tr[2] = (unsigned long long)world; tr[3] = (unsigned long long)h->mg.rank;
+			tr[4] = (unsigned long long)C; tr[5] = (unsigned long long)chunk_max; tr[6] = (unsigned long long)(ms * 1e6); tr[7] = 0;
+			CU(h, cudaMemcpy(tr.data() + 8, reinterpret_cast<char*>(h->mg.block) + l.off_trace, (size_t)loc[q].njobs * 32, cudaMemcpyDeviceToHost));
+			CU(h, cudaMemset(reinterpret_cast<char*>(h->mg.block) + l.off_trace, 0, (size_t)loc[q].njobs * 32));
+			std::string fn = std::string(getenv("B200_TRACE_DIR")) + "/trace_rank" + std::to_string(h->mg.rank) + ".bin";
+			if (FILE* f = fopen(fn.c_str(), "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
+		}
 		// re-arm this GPU's exchange block for the next chained call (everything that writes into it has finished: its
 		// only producers are the jobs on its left, all consumed; running-best pushes of slower peers go to this call's
 		// word, the NEXT call's word is reset here)

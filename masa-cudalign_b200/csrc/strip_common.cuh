@@ -113,6 +113,8 @@ struct StripParams {
 	long long watchdog_ns;  // a dependency that shows no progress for this long stops the kernel with an error (0 = never)
 	int* sm_load;           // chain mode: [0] warps inside compute segments on this GPU, [1 + 4 * smid + scheduler] the same per warp scheduler
 	int nsm;                // SMs of this GPU
+	unsigned long long* trace;   // development: per job {pushed, popped, first publication, finished} in globaltimer ns, or NULL
+	unsigned long long* nx_trace;   // the same array on the GPU that owns the chunks on our right
 	int test_delay_ms;      // test hook: the first job sleeps this long before it starts (tests/test_watchdog_gpu.py)
 	ChainParams chain;
 };
@@ -264,6 +266,7 @@ __device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
 				while ((job = ld_acquire_sys(p.chain.queue + head)) < 0) {                // the tail moves before the entry is stored
 					if (wd.expired(p, -1, 3)) { job = -1; break; }
 				}
+				if (p.trace && job >= 0) p.trace[4 * (size_t)job + 1] = global_ns();
 				break;
 			}
 			if (wd.expired(p, tail, 3)) break;
@@ -275,31 +278,37 @@ __device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
 }
 // top event: job (strip, k) has published its first columns, so (strip+1, k) may follow it (lane 0 only)
 // (out of line and fed with scalars only: a reference to the kernel parameters would force a local copy of them)
-__device__ __noinline__ void chain_notify_below_(unsigned long long* events, int* queue, int* tail, int nstrips, int job) {
+__device__ __noinline__ void chain_notify_below_(unsigned long long* events, int* queue, int* tail, int nstrips, int job, unsigned long long* trace) {
 	const int k = job / nstrips, r = job - k * nstrips;
+	if (trace) trace[4 * (size_t)job + 2] = global_ns();
 	if (r + 1 >= nstrips) return;
 	const unsigned long long old = atomicAdd_system(events + r + 1, 1ULL);
-	if ((unsigned)(old & 0xffffffffu) == (unsigned)k && (unsigned)(old >> 32) >= (unsigned)k + 1u)
+	if ((unsigned)(old & 0xffffffffu) == (unsigned)k && (unsigned)(old >> 32) >= (unsigned)k + 1u) {
+		if (trace) trace[4 * (size_t)(job + 1)] = global_ns();
 		chain_push(queue, tail, job + 1);
+	}
 }
 __device__ __forceinline__ void chain_notify_below(const StripParams& p, int job) {
-	chain_notify_below_(p.chain.events, p.chain.queue, p.chain.q_tail, p.chain.nstrips, job);
+	chain_notify_below_(p.chain.events, p.chain.queue, p.chain.q_tail, p.chain.nstrips, job, p.trace);
 }
 // left event: job (strip, chunk c) has stored its right border into the next GPU's exchange block, so (strip, c+1) may
 // start over there (lane 0 only; the border stores of the other lanes are ordered by the __syncwarp of the caller)
 __device__ __noinline__ void chain_notify_right_(const ChunkCol* chunks, unsigned long long* nx_events, int* nx_queue, int* nx_tail,
-                                                 int nstrips, int nchunks_total, int world, int job) {
+                                                 int nstrips, int nchunks_total, int world, int job, unsigned long long* trace, unsigned long long* nx_trace) {
 	const int k = job / nstrips, r = job - k * nstrips;
 	const int gidx = chunks[k].gidx;
+	if (trace) trace[4 * (size_t)job + 3] = global_ns();
 	if (gidx + 1 >= nchunks_total) return;
 	const int kn = (gidx + 1) / world;                 // local index of chunk c+1 on its owner
 	__threadfence_system();
 	const unsigned long long old = atomicAdd_system(nx_events + r, 1ULL << 32);
-	if ((unsigned)(old >> 32) == (unsigned)kn && (unsigned)(old & 0xffffffffu) >= (unsigned)kn + 1u)
+	if ((unsigned)(old >> 32) == (unsigned)kn && (unsigned)(old & 0xffffffffu) >= (unsigned)kn + 1u) {
+		if (nx_trace) nx_trace[4 * (size_t)(kn * nstrips + r)] = global_ns();
 		chain_push(nx_queue, nx_tail, kn * nstrips + r);
+	}
 }
 __device__ __forceinline__ void chain_notify_right(const StripParams& p, int job) {
-	chain_notify_right_(p.chain.chunks, p.chain.nx_events, p.chain.nx_queue, p.chain.nx_tail, p.chain.nstrips, p.chain.nchunks_total, p.chain.world, job);
+	chain_notify_right_(p.chain.chunks, p.chain.nx_events, p.chain.nx_queue, p.chain.nx_tail, p.chain.nstrips, p.chain.nchunks_total, p.chain.world, job, p.trace, p.nx_trace);
 }
 
 // next job of this launch, or -1 (all lanes return the same value)
