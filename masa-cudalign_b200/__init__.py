@@ -426,5 +426,6 @@ class Group:
         for r in range(len(self.devices)):
             res = Result()
             self.lib.b200_group_rank_result(self.g, r, C.byref(res))
-            out.append(dict(best=(res.best.score, res.best.i, res.best.j), cells=res.cells, cells_total=res.cells_total, device_ms=res.device_ms))
+            out.append(dict(best=(res.best.score, res.best.i, res.best.j), cells=res.cells, cells_total=res.cells_total, device_ms=res.device_ms,
+                            warp_busy=res.reserved[2] / 1000.0, warps=res.reserved[3]))
         return out

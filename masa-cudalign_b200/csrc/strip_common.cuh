@@ -249,9 +249,9 @@ __device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
 		Watchdog wd;
 		const unsigned slot_id = sched_slot();
 		int refused = 0;
-		// Idle back-off: 0.5 us doubling to 8 us.  Measured with tools/chain_perf.py on an under-filled GPU (592 strips, 2368
-		// resident warps): a 64 us ceiling is 7 % slower than 8 us -- every strip is re-dispatched once per chunk and the
-		// strips below it follow in lockstep, so pick-up latency is paid along the whole front.
+		// Idle back-off: 0.5 us doubling to 2 us.  Pick-up latency is part of the start-to-start distance of consecutive
+		// strips (a strip may start once the one above has published its first columns), which is paid once per strip while
+		// the front ramps up: measured with tools/chain_perf.py, a 64 us ceiling is 7 % slower than 8 us.
 		unsigned nap = 500;
 		for (;;) {
 			const int head = ld_relaxed(p.job_counter);
@@ -271,7 +271,7 @@ __device__ __forceinline__ int chain_pop(const StripParams& p, int lane) {
 			}
 			if (wd.expired(p, tail, 3)) break;
 			__nanosleep(nap);
-			if (nap < 8000) nap *= 2;
+			if (nap < 2000) nap *= 2;
 		}
 	}
 	return __shfl_sync(0xffffffffu, job, 0);

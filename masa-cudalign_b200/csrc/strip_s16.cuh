@@ -185,20 +185,7 @@ struct StripS16 {
 				smax_out = smax;
 				s.blk = __vmaxs2(s.blk, smax);
 			}
-			if (CHECK && jb.right_off >= 0) {
-				Cell* rb = right_border(p, cx);
-				if (col_lo == jb.cols - 1) {
-#pragma unroll
-					for (int r = 0; r < R; r++)
-						if (r < nv_lo) stcg_cell(rb + 1 + (2 * lane) * R + r, lo16(s.T[r]) + kGapFirst + s.base, lo16(s.E[r]) + s.base);
-					if (lane == 0) { const int cv = hi16(shH); __stcg(&rb[0].h, cv <= kNeg ? -kInf : cv + s.base); }   // corner for the block on our right
-				}
-				if (col_hi == jb.cols - 1) {
-#pragma unroll
-					for (int r = 0; r < R; r++)
-						if (r < nv_hi) stcg_cell(rb + 1 + (2 * lane + 1) * R + r, hi16(s.T[r]) + kGapFirst + s.base, hi16(s.E[r]) + s.base);
-				}
-			}
+			// (the right border is stored after the last step of the strip, from the frozen registers: run_job)
 		}
 		if (TRACK) {
 			// Rare path, deferred: a lane whose column pair ties/beats the best known so far parks its R packed
@@ -500,6 +487,7 @@ struct StripS16 {
 					const int c = tb + lane;
 					Cell tv; tv.h = -kInf; tv.x = -kInf;
 					if (c < cols && !top_minf) tv = ldcg_cell(p.busH + j0 + c);
+					if (c == cols - 1 && jb.right_off >= 0) __stcg(&right_border(p, cx)[0].h, tv.h);   // corner cell of the block on our right
 					if (prune && tb > c0) {
 						// stop the segment here if nothing entering [tb, ...) can still reach the best known score
 						int tmax = __reduce_max_sync(0xffffffffu, c < cols ? tv.h : 0);
@@ -582,7 +570,18 @@ struct StripS16 {
 				atomicAdd(p.cells_done + 1, global_ns() - seg_t0);
 				if (chained && p.sm_load != nullptr) { atomicSub(p.sm_load, 1); atomicSub(p.sm_load + 1 + sched_slot(), 1); }
 			}
-			if (c1 >= cols) break;
+			if (c1 >= cols) {
+				// the segment ran to the last column: every half froze when it passed it, so the registers hold column cols-1
+				if (jb.right_off >= 0) {
+					Cell* rb = right_border(p, cx);
+#pragma unroll
+					for (int r = 0; r < R; r++) {
+						if (r < nv_lo) stcg_cell(rb + 1 + rb_lo + r, lo16(s.T[r]) + kGapFirst + s.base, lo16(s.E[r]) + s.base);
+						if (r < nv_hi) stcg_cell(rb + 1 + rb_hi + r, hi16(s.T[r]) + kGapFirst + s.base, hi16(s.E[r]) + s.base);
+					}
+				}
+				break;
+			}
 			pos = c1;                          // the segment was cut short: continue in skip mode
 			computing = false;
 			lpend = INT_MIN;

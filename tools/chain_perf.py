@@ -26,6 +26,7 @@ ap.add_argument("--chunk", type=int, default=65536)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--modes", default="single,chain")
 ap.add_argument("--warps-per-sm", type=int, default=0)
+ap.add_argument("--group", type=int, default=0, help="mode 'group': this many ranks share device 0, each with 16/N warps per SM")
 args = ap.parse_args()
 if args.config:
     a, b = synth.make_config(args.config, args.scale)
@@ -35,6 +36,18 @@ else:
 m, n = a.size, b.size
 out = {"m": m, "n": n, "prune": args.prune, "chunk": args.chunk}
 for mode in args.modes.split(","):
+    if mode == "group":
+        os.environ["B200_GROUP_WARPS_PER_SM"] = str(16 // args.group)
+        g = b200.Group([0] * args.group, m, n, args.chunk)
+        g.set_sequences(a, b)
+        for rep in range(args.reps):
+            best = g.align_partition(use_callbacks=False, prune=args.prune, chunk_cols=args.chunk)
+        per = g.rank_results()
+        out[mode] = {"best": best["best"], "ms": round(best["device_ms"], 1), "gcups_computed": round(best["cells"] / best["device_ms"] / 1e6, 1),
+                     "computed_frac": round(best["cells"] / (m * n), 3), "warp_busy": best["warp_busy"], "chunks": best["chunks"],
+                     "per_rank": [(round(p["device_ms"], 1), p["warp_busy"], round(p["cells"] / max(best["cells"], 1), 3)) for p in per]}
+        g.close()
+        continue
     al = b200.Aligner(warps_per_sm=args.warps_per_sm)
     if mode == "chain":
         al.mgpu_setup(None, 0, 1, m, n, args.chunk)
