@@ -141,6 +141,8 @@ enum StripOpt : int {
 	OPT_RELEASE_128   = 4,   // after the first 2048 columns release the progress counter every 128 columns, not every 32
 	OPT_BEST_EVERY_4  = 8,   // exchange the running best with global_best every 4th block
 	OPT_SKIP_128      = 16,  // skip mode decides 128 columns at a time when the strip above is that far ahead
+	OPT_LOOKAHEAD     = 32,  // a strip that has to wait for the one above waits for two extra blocks (fewer spin-waits at the same pace)
+	OPT_DEFER_RELEASE = 64,  // steady state: publish a block's counter one block later, when its stores have long landed
 };
 
 __device__ __forceinline__ int ld_acquire(const int* p) {

@@ -475,7 +475,12 @@ struct StripS16 {
 					const int need = tb + 32 < cols ? tb + 32 : cols;
 					if (!(opt & OPT_SEEN_CACHE)) wait_progress(p, jb.dep, cx.prog_base + need, lane);
 					else if (seen < need) {
-						seen = wait_progress_v(p, jb.dep, cx.prog_base + need, lane) - cx.prog_base;
+						// Look-ahead (OPT_LOOKAHEAD): a strip that has caught up with the one above would find every block
+						// "just not ready" and pay the detection latency of a spin-wait per block; waiting for two more blocks
+						// instead lets it run the next ones without touching the counter (same pace, a third of the waits).
+						int want = need;
+						if ((opt & OPT_LOOKAHEAD) && tb >= c0 + 256) want = need + 64 < cols ? need + 64 : cols;
+						seen = wait_progress_v(p, jb.dep, cx.prog_base + want, lane) - cx.prog_base;
 						if (seen < need) return;       // the kernel is stopping (watchdog)
 					}
 					if (TRACK && p.track == 2 && (!(opt & OPT_BEST_EVERY_4) || (tb & 96) == 0 || tb == c0)) {
@@ -543,6 +548,12 @@ struct StripS16 {
 				int cdone = tb + 31 - vo; cdone = cdone < c1 - 1 ? cdone : c1 - 1;
 				if (cdone >= flushed) {
 					__syncwarp();
+					// Deferred release (OPT_DEFER_RELEASE): in the steady part of a segment the counter published here is the one
+					// of the PREVIOUS block -- its stores landed 32 steps ago, so the fence inside st.release has nothing to wait
+					// for (a release right behind the stores stalls the warp for an L2 round trip, every block, on the critical
+					// path of every strip chained below).  The ramp-up (first 256 columns) and the end of a segment publish at once.
+					const bool now = !(opt & OPT_DEFER_RELEASE) || cdone < 256 || cdone + 1 == cols || tb + 32 >= c1;
+					if (!now && lane == 0) st_release(p.progress + cx.pidx, cx.prog_base + flushed);
 					for (int c = flushed + lane; c <= cdone; c += 32) {
 						const int k = c - tb + vo;                 // step of this block that completed column c of the bottom row
 						const unsigned px = sm.botH[k], py = sm.botF[k];
@@ -553,9 +564,9 @@ struct StripS16 {
 					}
 					// the strips below start as soon as the first columns are out; once the chain is filled the counter is
 					// released every 128 columns (a release costs a fence; the consumers run several blocks behind anyway)
-					const bool rel = !(opt & OPT_RELEASE_128) || cdone + 1 == cols || cdone < 2048 || tb + 32 >= c1 ||
-					                 ((cdone + 1) >> 7) != (flushed >> 7);
-					const bool first = chained && flushed == 0;      // (the first release is never deferred: cdone < 2048)
+					const bool rel = now && (!(opt & OPT_RELEASE_128) || cdone + 1 == cols || cdone < 2048 || tb + 32 >= c1 ||
+					                         ((cdone + 1) >> 7) != (flushed >> 7));
+					const bool first = chained && flushed == 0;      // (the first release is never deferred: cdone < 256)
 					flushed = cdone + 1;
 					__syncwarp();
 					if (rel && lane == 0) {

@@ -159,10 +159,10 @@ def chain_case():
     return a, b, ids, O.full_matrix(a, b, O.SW, row_ids=[i - 1 for i in ids])   # the oracle runs once for all variants
 
 
-@pytest.mark.parametrize("opt", [0, 1, 2, 3, 7, 15, 27, 31])
+@pytest.mark.parametrize("opt", [0, 1, 2, 3, 7, 15, 27, 31, 32 + 27, 64 + 27, 96 + 27, 96 + 31])
 def test_chain_protocol_variants_are_exact(b200, opt, chain_case, monkeypatch):
     """Every StripOpt combination (csrc/strip_common.cuh: fence choice, cached progress, 128-column releases, best
-    exchange every 4th block, 128-column skips) only changes how often the strip chain synchronises: results stay
+    exchange every 4th block, 128-column skips, look-ahead waits, deferred releases) only changes how often the strip chain synchronises: results stay
     bit-exact without pruning, and the best cell stays exact with pruning."""
     a, b, ids, o = chain_case
     monkeypatch.setenv("B200_OPT", str(opt))
