@@ -22,6 +22,7 @@ B200Aligner::B200Aligner() {
 	score_params.gap_open = 3;
 	score_params.gap_ext = 2;
 	handle = NULL;
+	group = NULL; groupRows = groupJobs = 0; groupSeqValid = false; seq0_ptr = seq1_ptr = NULL; groupPartitions = 0;
 	multiprocessors = 148;
 	seq0_len = seq1_len = 0;
 	fastActive = false;
@@ -57,7 +58,7 @@ aligner_capabilities_t B200Aligner::getCapabilities() {
 	c.dispatch_scores = SUPPORTED;
 	c.process_partition = SUPPORTED;
 	c.variable_penalties = NOT_SUPPORTED;
-	c.fork_processes = NOT_SUPPORTED;               /* multi-GPU = in-kernel NVLink chain (b200_mgpu_*), not fork()+sockets */
+	c.fork_processes = NOT_SUPPORTED;               /* multi-GPU = --gpus=N: in-kernel NVLink chain (b200_group_*), not fork()+sockets */
 	c.maximum_seq0_len = 0;                         /* no 2^27 texture limit (R/src/CUDAligner.cpp:41-44) */
 	c.maximum_seq1_len = 0;
 	return c;
@@ -67,9 +68,10 @@ IAlignerParameters* B200Aligner::getParameters() { return params; }
 const score_params_t* B200Aligner::getScoreParameters() { return &score_params; }
 
 void B200Aligner::initialize() {
+	if (params->getGpuList().size() > 1) return;   /* --gpus: the group is created by the first setSequences (it is sized by the sequences) */
 	b200_config cfg;
 	memset(&cfg, 0, sizeof(cfg));
-	cfg.device = params->getGPU() < 0 ? 0 : params->getGPU();
+	cfg.device = params->getGpuList().size() == 1 ? params->getGpuList()[0] : (params->getGPU() < 0 ? 0 : params->getGPU());
 	cfg.kernel = params->getKernel();
 	int rc = b200_create(&cfg, &handle);
 	if (rc != 0) {
@@ -80,6 +82,11 @@ void B200Aligner::initialize() {
 }
 
 void B200Aligner::finalize() {
+	if (group != NULL) {
+		if (g_active_handle == handle) g_active_handle = NULL;
+		b200_group_destroy(group);          /* owns every handle, including `handle` */
+		group = NULL; handle = NULL;
+	}
 	if (handle != NULL) {
 		if (g_active_handle == handle) g_active_handle = NULL;
 		b200_destroy(handle);
@@ -87,9 +94,36 @@ void B200Aligner::finalize() {
 	}
 }
 
+/* --gpus=N: (re)create the group when the sequences need a larger exchange block than the current one has */
+void B200Aligner::ensureGroup() {
+	b200_partition whole;
+	memset(&whole, 0, sizeof(whole));
+	whole.i1 = seq0_len; whole.j1 = seq1_len;
+	b200_chain_info info;
+	const std::vector<int>& devs = params->getGpuList();
+	if (b200_chain_plan(&whole, (int)devs.size(), &info) != 0) { fprintf(stderr, "B200Aligner: b200_chain_plan failed\n"); exit(-1); }
+	if (group != NULL && seq0_len <= groupRows && info.max_jobs <= groupJobs) return;
+	if (group != NULL) { if (g_active_handle == handle) g_active_handle = NULL; b200_group_destroy(group); group = NULL; handle = NULL; }
+	b200_config cfg;
+	memset(&cfg, 0, sizeof(cfg));
+	cfg.kernel = params->getKernel();
+	groupRows = seq0_len; groupJobs = info.max_jobs;
+	int rc = b200_group_create(&devs[0], (int)devs.size(), &cfg, groupRows, groupJobs, &group);
+	if (rc != 0) {
+		fprintf(stderr, "B200Aligner: cannot initialise the GPU group: %s\n", b200_group_last_error(NULL));
+		exit(-1);
+	}
+	handle = b200_group_handle(group, 0);
+	g_active_handle = handle;
+}
+
 void B200Aligner::setSequences(const char* seq0, const char* seq1, int seq0_len, int seq1_len) {
 	this->seq0_len = seq0_len;
 	this->seq1_len = seq1_len;
+	seq0_ptr = seq0; seq1_ptr = seq1;
+	if (params->getGpuList().size() > 1) ensureGroup();
+	/* the other GPUs of a group receive the sequences only when a partition is large enough to use them (useGroupFor) */
+	groupSeqValid = false;
 	check(b200_set_sequences(handle, seq0, seq0_len, seq1, seq1_len), "b200_set_sequences");
 	rowBuffer.resize((size_t)seq1_len + 2);
 }
@@ -240,6 +274,15 @@ void B200Aligner::alignPartitionChunked(Partition partition) {
 	fastActive = false;
 }
 
+/* Partitions worth the chain: stage 1 of a big comparison.  Small ones (stage 3, short sequences) would spend longer
+ * filling the multi-GPU pipeline than computing. */
+bool B200Aligner::useGroupFor(Partition partition) {
+	if (group == NULL) return false;
+	long long min_cells = 20000000000LL;
+	if (const char* e = getenv("B200_GROUP_MIN_CELLS")) min_cells = atoll(e);      /* tests: small partitions through the chain */
+	return (long long)partition.getHeight() * (long long)partition.getWidth() >= min_cells;
+}
+
 void B200Aligner::alignPartitionFast(Partition partition) {
 	fastPartitions++;
 	fastPartition = partition;
@@ -247,6 +290,13 @@ void B200Aligner::alignPartitionFast(Partition partition) {
 	b200_partition p;
 	fillPartition(p, partition);
 	p.want_last_column = 0;
+	const bool chain = useGroupFor(partition);
+	if (chain) { if (const char* e = getenv("B200_CHAIN_CHUNK")) p.reserved[1] = atoi(e); }     /* chunk width override (tests) */
+	if (chain && !groupSeqValid) {
+		for (int r = 1; r < b200_group_size(group); r++)
+			check(b200_set_sequences(b200_group_handle(group, r), seq0_ptr, seq0_len, seq1_ptr, seq1_len), "b200_set_sequences (group)");
+		groupSeqValid = true;
+	}
 
 	b200_callbacks cb;
 	memset(&cb, 0, sizeof(cb));
@@ -258,7 +308,15 @@ void B200Aligner::alignPartitionFast(Partition partition) {
 	cb.dispatch_score = cbDispatchScore;
 	cb.must_continue = cbMustContinue;
 	b200_result res;
-	check(b200_align_partition(handle, &p, &cb, &res), "b200_align_partition");
+	if (chain) {
+		groupPartitions++;
+		if (b200_group_align_partition(group, &p, &cb, &res) != 0) {
+			fprintf(stderr, "B200Aligner: b200_group_align_partition failed: %s\n", b200_group_last_error(group));
+			exit(-1);
+		}
+	} else {
+		check(b200_align_partition(handle, &p, &cb, &res), "b200_align_partition");
+	}
 	fastCells += res.cells;
 	fastDeviceMs += res.device_ms;
 	fastActive = false;
@@ -425,7 +483,11 @@ void B200Aligner::clearStatistics() {
 }
 
 void B200Aligner::printInitialStatistics(FILE* file) {
-	fprintf(file, "B200 aligner extension: %d CUDA device(s), using GPU %d\n", b200_device_count(), params->getGPU() < 0 ? 0 : params->getGPU());
+	if (params->getGpuList().size() > 1) {
+		fprintf(file, "B200 aligner extension: %d CUDA device(s), stage-1 chain over %d GPUs (first:", b200_device_count(), (int)params->getGpuList().size());
+		fprintf(file, " %d)\n", params->getGpuList()[0]);
+	} else
+		fprintf(file, "B200 aligner extension: %d CUDA device(s), using GPU %d\n", b200_device_count(), params->getGPU() < 0 ? 0 : params->getGPU());
 }
 
 void B200Aligner::printStageStatistics(FILE* file) {
@@ -433,8 +495,8 @@ void B200Aligner::printStageStatistics(FILE* file) {
 }
 
 void B200Aligner::printFinalStatistics(FILE* file) {
-	fprintf(file, "B200 partitions: %lld whole-partition (persistent kernel), %lld chunked (%lld launches), %lld per-diagonal; kernel launches: %lld\n",
-			fastPartitions, chunkPartitions, chunkLaunches, diagPartitions, handle ? b200_kernel_launches(handle) : 0LL);
+	fprintf(file, "B200 partitions: %lld whole-partition (persistent kernel; %lld of them on the multi-GPU chain), %lld chunked (%lld launches), %lld per-diagonal; kernel launches: %lld\n",
+			fastPartitions, groupPartitions, chunkPartitions, chunkLaunches, diagPartitions, handle ? b200_kernel_launches(handle) : 0LL);
 }
 
 void B200Aligner::printStatistics(FILE* file) {

@@ -65,7 +65,12 @@ protected:
 private:
 	B200AlignerParameters* params;
 	score_params_t score_params;
-	b200_handle* handle;
+	b200_handle* handle;            /* the GPU of stages 2-6 and of small partitions (rank 0 of the group with --gpus) */
+	b200_group* group;              /* --gpus=N: the GPUs of the stage-1 chain (created when the sequence sizes are known) */
+	long long groupRows, groupJobs; /* capacity the group was created for */
+	bool groupSeqValid;             /* the current sequences are resident on every GPU of the group */
+	const char* seq0_ptr; const char* seq1_ptr;
+	long long groupPartitions;
 	int multiprocessors;
 	int seq0_len, seq1_len;
 	bool fastActive;
@@ -86,6 +91,8 @@ private:
 	bool canUseFastPath();
 	bool canUseChunkPath();
 	void alignPartitionFast(Partition partition);
+	bool useGroupFor(Partition partition);
+	void ensureGroup();
 	void alignPartitionChunked(Partition partition);
 	void fillPartition(b200_partition& p, Partition partition);
 

@@ -12,6 +12,10 @@
 --gpu=GPU               Selects the index of the GPU used for the computation.  \n\
                            Default: GPU 0. See --list-gpus. \n\
 --list-gpus             Lists all available GPUs. \n\
+--gpus=N | --gpus=A,B,..  Stage 1 on several GPUs of this box (NVLink chain: column  \n\
+                           chunks dealt round-robin, borders through peer memory,    \n\
+                           block pruning stays on). Stages 2-6 use the first one.    \n\
+                           Replaces the reference's --fork/--split for one box.      \n\
 --blocks=B              Run B blocks per external diagonal (compatibility path). \n\
 --kernel=auto|s32|s16x2 DP kernel: packed s16x2 DPX lanes (ACGT inputs) or exact \n\
                            int32 lanes (any alphabet). Default: auto. \n\
@@ -23,6 +27,7 @@
 #define ARG_BLOCKS     0x1003
 #define ARG_KERNEL     0x1004
 #define ARG_NO_FAST    0x1005
+#define ARG_GPUS       0x1006
 
 static struct option long_options[] = {
 	{"gpu",          required_argument, 0, ARG_GPU},
@@ -30,6 +35,7 @@ static struct option long_options[] = {
 	{"blocks",       required_argument, 0, ARG_BLOCKS},
 	{"kernel",       required_argument, 0, ARG_KERNEL},
 	{"no-fast-path", no_argument,       0, ARG_NO_FAST},
+	{"gpus",         required_argument, 0, ARG_GPUS},
 	{0, 0, 0, 0}
 };
 
@@ -73,6 +79,20 @@ int B200AlignerParameters::processArgument(int argc, char** argv) {
 		break;
 	case ARG_NO_FAST:
 		fastPath = false;
+		break;
+	case ARG_GPUS:
+		if (optarg != NULL) {
+			gpuList.clear();
+			if (strchr(optarg, ',') != NULL) {
+				std::stringstream in(optarg);
+				std::string tok;
+				while (std::getline(in, tok, ',')) gpuList.push_back(atoi(tok.c_str()));
+			} else {
+				int n = atoi(optarg);
+				for (int k = 0; k < n; k++) gpuList.push_back((gpu < 0 ? 0 : gpu) + k);
+			}
+			if (gpuList.empty() || gpuList.size() > 8) { setLastError("--gpus takes 1..8 GPUs."); return -1; }
+		}
 		break;
 	default:
 		return ret;

@@ -24,9 +24,11 @@ def _need_binaries():
         pytest.skip("build/cudalign or oracle/_ref binaries not built (need the reference mount at build time)")
 
 
-def _run(exe, fa, fb, wd, extra):
+def _run(exe, fa, fb, wd, extra, env=None):
     cmd = [exe, f"--work-dir={wd}", "--clear", "--verbose=0", *extra, fa, fb]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200)
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200, env=e)
     assert r.returncode == 0, f"{' '.join(cmd)}\n{r.stdout[-3000:]}"
 
 
@@ -83,3 +85,36 @@ def test_full_pipeline_matches_reference(tmp_path, name, m, n, hom, extra, sr, p
     nrows = _compare(w_ref, w_new, sr)
     if sr:
         assert nrows > 0
+
+
+MGPU_CASES = [
+    ("sw_40k_nopruning_disk", 40000, 39979, (5000, 35000), ["--no-block-pruning", "--disk-size=4M"], True),
+    ("sw_40k_pruning_ram", 40000, 39979, (5000, 35000), ["--ram-size=3M"], False),
+    ("nw_global_20k", 20000, 21000, (0, 20000), ["--alignment-edges=++", "--disk-size=4M", "--no-block-pruning"], True),
+    ("sw_150k_pruning", 150000, 140000, (20000, 120000), ["--disk-size=40M"], False),
+]
+
+
+@pytest.mark.parametrize("name,m,n,hom,extra,sr", MGPU_CASES, ids=[c[0] for c in MGPU_CASES])
+@pytest.mark.parametrize("gpus", ["0,0", "0,0,0,0"])
+def test_multi_gpu_pipeline_matches_reference(tmp_path, name, m, n, hom, extra, sr, gpus):
+    """build/cudalign --gpus=...: stage 1 on the block-cyclic chain (here: several ranks sharing device 0; with real
+    device lists the same code path runs over NVLink, tests/test_mgpu_gpu.py), stages 2-6 on the first GPU.  The
+    artefacts must be the reference's, byte for byte -- special rows included: they are assembled from the chunks of all
+    ranks before they reach MASA-Core's special-rows area."""
+    _need_binaries()
+    a, b = synth.make_pair(m, n, [hom], 0.05, 0.02, 0.02, 0, 11)
+    fa, fb = str(tmp_path / "A.fa"), str(tmp_path / "B.fa")
+    synth.write_fasta(fa, a, "A")
+    synth.write_fasta(fb, b, "B")
+    w_ref, w_new = str(tmp_path / "ref"), str(tmp_path / "new")
+    _run(os.path.join(O.REF_DIR, "oracle_cpu"), fa, fb, w_ref, extra)
+    nranks = gpus.count(",") + 1
+    _run(CUDALIGN, fa, fb, w_new, extra + [f"--gpus={gpus}"],
+         env={"B200_GROUP_WARPS_PER_SM": str(16 // nranks), "B200_GROUP_MIN_CELLS": "0", "B200_CHAIN_CHUNK": "3000", "B200_WATCHDOG_S": "30"})
+    sp = os.path.join(w_new, "statistics.ALIGNER")        # printFinalStatistics (libmasa.cpp:1336,1398)
+    stats = open(sp).read() if os.path.exists(sp) else ""
+    nrows = _compare(w_ref, w_new, sr)
+    if sr:
+        assert nrows > 0
+    assert "on the multi-GPU chain" in stats and " 0 of them on the multi-GPU chain" not in stats, "stage 1 did not take the chain"
