@@ -201,7 +201,9 @@ __global__ void match_column_kernel(const Cell* buffer, const Cell* base, int le
 // warps that fit (5M x 5M without pruning: 4083 GCUPS at 11 warps/SM, 4426 at 16; profiles/r01_protocol_options.txt).
 constexpr int kSatWarps = 16;
 // protocol variant of the strip chain (StripOpt bits); B200_OPT overrides the default for experiments
-constexpr int kDefaultStripOpt = OPT_NO_SC_FENCE | OPT_SEEN_CACHE | OPT_BEST_EVERY_4 | OPT_SKIP_128 | OPT_LOOKAHEAD | OPT_DEFER_RELEASE;   // measured: profiles/r01_protocol_options.txt; OPT_RELEASE_128 is within noise at 5M x 5M and lengthens the pipeline fill of narrow partitions
+// OPT_LOOKAHEAD / OPT_DEFER_RELEASE (round 2) are exact too but bought nothing: 2813 / 2844 / 2797 / 2831 ms for the four
+// combinations on a pruned 3.45M x 3.75M run, 567 / 590 / 568 / 599 ms on a 4-rank chain (profiles/r02_chain_starvation.txt)
+constexpr int kDefaultStripOpt = OPT_NO_SC_FENCE | OPT_SEEN_CACHE | OPT_BEST_EVERY_4 | OPT_SKIP_128;   // measured: profiles/r01_protocol_options.txt; OPT_RELEASE_128 is within noise at 5M x 5M and lengthens the pipeline fill of narrow partitions
 int strip_opt() {
 	const char* e = getenv("B200_OPT");      // read per launch: experiments switch it between runs of one process
 	return e ? atoi(e) : kDefaultStripOpt;
