@@ -416,7 +416,8 @@ def main():
     }
     if e2e_times:
         line["e2e"] = {"value": m * n * len(e2e_times) / e2e_total / 1e9, "unit": "GCUPS", "steps": len(e2e_times),
-                       "h2d_bytes_per_step": int(m + n) * args.gpus, "d2h_bytes_per_step": int(strips * 16 + 32) * args.gpus}
+                       # pure A/C/G/T sequences cross PCIe 2-bit packed (16 bases per 32-bit word), once per GPU
+                       "h2d_bytes_per_step": 4 * ((m + 15) // 16 + (n + 15) // 16) * args.gpus, "d2h_bytes_per_step": int(strips * 16 + 32) * args.gpus}
     if world == 1 and not args.no_full_alignment:
         with tempfile.TemporaryDirectory() as td:
             line["full_alignment"] = full_alignment_leg(td)

@@ -66,8 +66,12 @@ struct b200_handle {
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	std::string err;
 
-	// sequences (device, 1 byte per base like the reference: R/src/cuda_util.cpp:50-56)
+	// sequences on the device: 2 bits per base for pure A/C/G/T inputs (what the packed kernel reads; only these words
+	// cross PCIe) plus the byte view of the reference (R/src/cuda_util.cpp:50-56) for the int32 kernel, rebuilt on the device
 	DevBuf<unsigned char> s0, s1;
+	DevBuf<unsigned> s0p, s1p;
+	PinBuf<unsigned> hpack;
+	bool packed = false;
 	int n0 = 0, n1 = 0;
 	bool acgt_only = false;
 	std::vector<unsigned char> bad0;   // per 64 rows of seq0: 1 when the block holds a non-ACGT byte (forces the int32 strip path)
@@ -246,6 +250,7 @@ int grid_for(b200_handle* h, const void* kernel, int njobs, bool chained) {
 int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kernel_kind, int SH, bool chained) {
 	StripParams sp;
 	sp.s0 = h->ov.s0 ? h->ov.s0 : h->s0.p; sp.s1 = h->ov.s1 ? h->ov.s1 : h->s1.p;
+	sp.s0p = (h->packed && !h->ov.s0) ? h->s0p.p : nullptr; sp.s1p = (h->packed && !h->ov.s1) ? h->s1p.p : nullptr;
 	sp.busH = h->ov.busH ? h->ov.busH : h->busH.p; sp.sra = h->sra.p;
 	sp.left = h->ov.left ? h->ov.left : h->left.p;
 	sp.right = h->ov.no_right ? nullptr : (h->ov.right ? h->ov.right : h->right.p);
@@ -368,7 +373,7 @@ extern "C" void b200_destroy(b200_handle* h) {
 	if (!h) return;
 	cudaSetDevice(h->cfg.device);
 	cudaStreamSynchronize(h->stream);
-	h->s0.release(); h->s1.release(); h->busH.release(); h->left.release(); h->right.release(); h->sra.release();
+	h->s0.release(); h->s1.release(); h->s0p.release(); h->s1p.release(); h->hpack.release(); h->busH.release(); h->left.release(); h->right.release(); h->sra.release();
 	h->jobs.release(); h->progress.release(); h->results.release(); h->scalars.release();
 	h->hcells.release(); h->hresults.release(); h->hscalars.release();
 	h->matchbuf.release(); h->matchflag.release(); h->hmatchflag.release(); h->smload.release();
@@ -389,28 +394,62 @@ extern "C" long long b200_kernel_launches(const b200_handle* h) { return h ? h->
 // ---------------------------------------------------------------------------------------------------------
 // sequences
 // ---------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void unpack2_kernel(const unsigned* src, unsigned char* dst, int n) {
+	const int k = blockIdx.x * blockDim.x + threadIdx.x;
+	if (k < n) dst[k] = (unsigned char)("ACTG"[(src[k >> 4] >> ((k & 15) * 2)) & 3u]);      // code = (byte >> 1) & 3
+}
+// One pass over a host sequence: alphabet check + 2-bit packing (16 bases per word).  Returns false at the first
+// non-A/C/G/T byte (the words written so far are then meaningless).
+bool pack2(const char* s, int n, unsigned* out) {
+	int k = 0;
+	for (int w = 0; k < n; w++) {
+		unsigned v = 0;
+		const int lim = n - k < 16 ? n - k : 16;
+		for (int q = 0; q < lim; q++) {
+			const unsigned char c = (unsigned char)s[k + q];
+			if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) return false;
+			v |= (unsigned)((c >> 1) & 3) << (2 * q);
+		}
+		out[w] = v;
+		k += lim;
+	}
+	return true;
+}
+}  // namespace
+
 extern "C" int b200_set_sequences(b200_handle* h, const char* seq0, int seq0_len, const char* seq1, int seq1_len) {
 	if (!h) return 1;
 	if (!seq0 || !seq1 || seq0_len < 0 || seq1_len < 0) { h->err = "b200_set_sequences: bad arguments"; return 1; }
 	CU(h, cudaSetDevice(h->cfg.device));
 	CU(h, h->s0.reserve((size_t)seq0_len + 64));
 	CU(h, h->s1.reserve((size_t)seq1_len + 64));
-	CU(h, cudaMemcpyAsync(h->s0.p, seq0, (size_t)seq0_len, cudaMemcpyHostToDevice, h->stream));
-	CU(h, cudaMemcpyAsync(h->s1.p, seq1, (size_t)seq1_len, cudaMemcpyHostToDevice, h->stream));
-	// alphabet scan (host, vectorisable): the packed kernel handles exactly A,C,G,T
-	auto only_acgt = [](const char* s, int n) {
-		unsigned char bad = 0;
-		for (int k = 0; k < n; k++) { unsigned char c = (unsigned char)s[k]; bad |= (unsigned char)!(c == 'A' || c == 'C' || c == 'G' || c == 'T'); }
-		return bad == 0;
-	};
-	h->acgt_only = only_acgt(seq0, seq0_len) && only_acgt(seq1, seq1_len);
+	const size_t w0 = ((size_t)seq0_len + 15) / 16, w1 = ((size_t)seq1_len + 15) / 16;
+	CU(h, h->hpack.reserve(w0 + w1 + 2));
+	// FASTA bytes -> 2-bit words on the host (the reference keeps one byte per base, C/common/biology/SequenceData.cpp:67-114):
+	// pure A/C/G/T inputs cross PCIe packed and stay packed in HBM for the DPX kernel
+	h->acgt_only = pack2(seq0, seq0_len, h->hpack.p) && pack2(seq1, seq1_len, h->hpack.p + w0);
+	h->packed = h->acgt_only && !getenv("B200_NO_PACK");
 	h->bad0.assign((size_t)seq0_len / 64 + 2, 0);
-	if (!h->acgt_only)
-		for (int k = 0; k < seq0_len; k++) { unsigned char c = (unsigned char)seq0[k]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) h->bad0[k >> 6] = 1; }
+	if (h->packed) {
+		CU(h, h->s0p.reserve(w0 + 1));
+		CU(h, h->s1p.reserve(w1 + 1));
+		CU(h, cudaMemcpyAsync(h->s0p.p, h->hpack.p, w0 * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
+		CU(h, cudaMemcpyAsync(h->s1p.p, h->hpack.p + w0, w1 * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
+		if (seq0_len) unpack2_kernel<<<(seq0_len + 255) / 256, 256, 0, h->stream>>>(h->s0p.p, h->s0.p, seq0_len);
+		if (seq1_len) unpack2_kernel<<<(seq1_len + 255) / 256, 256, 0, h->stream>>>(h->s1p.p, h->s1.p, seq1_len);
+		h->stat_launches += 2;
+	} else {
+		CU(h, cudaMemcpyAsync(h->s0.p, seq0, (size_t)seq0_len, cudaMemcpyHostToDevice, h->stream));
+		CU(h, cudaMemcpyAsync(h->s1.p, seq1, (size_t)seq1_len, cudaMemcpyHostToDevice, h->stream));
+		if (!h->acgt_only)
+			for (int k = 0; k < seq0_len; k++) { unsigned char c = (unsigned char)seq0[k]; if (!(c == 'A' || c == 'C' || c == 'G' || c == 'T')) h->bad0[k >> 6] = 1; }
+	}
 	h->n0 = seq0_len; h->n1 = seq1_len;
 	h->s4.rev_valid = false;
 	CU(h, h->busH.reserve((size_t)seq1_len + 64));
 	CU(h, cudaStreamSynchronize(h->stream));
+	CU(h, cudaGetLastError());
 	return 0;
 }
 

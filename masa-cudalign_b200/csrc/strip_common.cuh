@@ -90,6 +90,8 @@ struct ChainParams {
 struct StripParams {
 	const unsigned char* s0;
 	const unsigned char* s1;
+	const unsigned* s0p;    // the same sequences packed 2 bits per base (16 bases per word, code = (byte >> 1) & 3: A 0, C 1, T 2, G 3),
+	const unsigned* s1p;    // or NULL (inputs with N / IUPAC bytes, stage-4 reversed copies): the packed kernel then reads the bytes
 	Cell* busH;             // [seq1_len] (H,F) of the row above the strip being read / bottom row being written
 	const Cell* left;       // left borders  (H,E)
 	Cell* right;            // right borders (H,E)
@@ -390,6 +392,8 @@ __device__ __forceinline__ int ld_uniform(const int* p) {
 	const int v = ld_relaxed(p);
 	return __shfl_sync(0xffffffffu, v, 0);
 }
+// base `idx` of a 2-bit packed sequence
+__device__ __forceinline__ int packed_code(const unsigned* sp, int idx) { return (int)((__ldg(sp + (idx >> 4)) >> ((idx & 15) * 2)) & 3u); }
 __device__ __forceinline__ Cell ldcg_cell(const Cell* p) {
 	int2 v = __ldcg(reinterpret_cast<const int2*>(p));
 	Cell c; c.h = v.x; c.x = v.y; return c;

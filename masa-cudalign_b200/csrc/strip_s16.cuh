@@ -324,11 +324,11 @@ struct StripS16 {
 		for (int r = 0; r < R; r++) {
 			int hl = -kGapFirst - base, el = kNeg, hh = -kGapFirst - base, eh = kNeg, cl = 0, chh = 0;
 			if (r < nv_lo) {
-				cl = code_of(p.s0[i0 + rb_lo + r]);
+				cl = (LUT && p.s0p) ? packed_code(p.s0p, i0 + rb_lo + r) : code_of(p.s0[i0 + rb_lo + r]);
 				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_lo + r); lmaxv = max(lmaxv, c.h); hl = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); el = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
 			} else { hl = kNeg; }
 			if (r < nv_hi) {
-				chh = code_of(p.s0[i0 + rb_hi + r]);
+				chh = (LUT && p.s0p) ? packed_code(p.s0p, i0 + rb_hi + r) : code_of(p.s0[i0 + rb_hi + r]);
 				if (!lz) { Cell c = ldcg_cell(lb + 1 + rb_hi + r); lmaxv = max(lmaxv, c.h); hh = clamp16(c.h < -kInf / 2 ? kNeg : c.h - kGapFirst - base); eh = clamp16(c.x < -kInf / 2 ? kNeg : c.x - base); }
 			} else { hh = kNeg; }
 			s.T[r] = pack2(clamp16(hl), clamp16(hh));
@@ -514,7 +514,8 @@ struct StripS16 {
 						if (c < cols) {
 							th = tv.h < -kInf / 2 ? kNeg : clamp16(tv.h - s.base);
 							tf = tv.x < -kInf / 2 ? kNeg : clamp16(tv.x - s.base);
-							pw = LUT ? (unsigned)code_of(p.s1[j0 + c]) << 11 : profile_word(p.s1[j0 + c]);   // LUT row offset of the column code, or profile word: byte k = 6 (match+5) / 2
+							if (LUT) pw = (unsigned)(p.s1p ? packed_code(p.s1p, j0 + c) : code_of(p.s1[j0 + c])) << 11;
+							else pw = profile_word(p.s1[j0 + c]);   // LUT row offset of the column code, or profile word: byte k = 6 (match+5) / 2
 						}
 						sm.top[lane] = make_uint4((unsigned)th << 16, (unsigned)tf << 16, pw, 0u);
 						__syncwarp();

@@ -178,3 +178,26 @@ def test_chain_protocol_variants_are_exact(b200, opt, chain_case, monkeypatch):
     assert rp["best"] == o["best"]
     assert rp["cells"] < r["cells"]
     al.close()
+
+
+@pytest.mark.parametrize("m,n", [(5000, 7001), (33, 15), (20000, 16)])
+def test_packed_and_byte_sequences_agree(b200, monkeypatch, m, n):
+    """Pure A/C/G/T inputs live 2-bit packed in HBM (16 bases per word) and the packed kernel reads those words; with
+    B200_NO_PACK the same kernel reads the byte arrays.  Both must match the oracle (odd lengths: partial last words)."""
+    a, b = _pair(m, n, 9)
+    o = O.full_matrix(a, b, O.SW, row_ids=[m - 1])
+    for no_pack in ("", "1"):
+        if no_pack:
+            monkeypatch.setenv("B200_NO_PACK", "1")
+        else:
+            monkeypatch.delenv("B200_NO_PACK", raising=False)
+        al = b200.Aligner(kernel=b200.KERNEL_S16X2)
+        al.set_sequences(a, b)
+        r = al.align_partition(want_last_row=True, want_last_column=True)
+        assert r["best"] == o["best"]
+        assert np.array_equal(r["rows"][m], o["rows"][m - 1])
+        assert np.array_equal(r["last_column"], o["last_col"])
+        r = al.align_partition(17 % m, 3 % n, m, n, want_last_row=True, use_callbacks=True, want_best_score=True)     # unaligned sub-partition
+        o2 = O.full_matrix(a[17 % m:], b[3 % n:], O.SW, row_ids=[m - 17 % m - 1])
+        assert r["best"] == (o2["best"][0], o2["best"][1] + 17 % m, o2["best"][2] + 3 % n)
+        al.close()
