@@ -143,6 +143,7 @@ struct b200_handle {
 	} s4;
 
 	Cell cont_corner;              // first-column cell of the last row of the previous chunk (B200_CONT_CHUNK)
+	bool cont_force32 = false;     // the chunked partition in progress runs the int32 kernel (-INF in an NW border)
 	int last_grid_warps = 0;
 	long long stat_cells = 0;
 	long long stat_launches = 0;
@@ -488,7 +489,7 @@ extern "C" int b200_special_row_ids(int height, int block_height, int interval, 
 // Strips of a partition: cut every kSH16F (packed) / kSH32 (int32) rows and additionally at the reference's special-row
 // ids, so that every special row is the bottom row of a strip.  Identical on every GPU of a chain.
 static void build_strips(b200_handle* h, const b200_partition* p, int m, const std::vector<int>& sr_ids,
-                         std::vector<StripRow>& rows, bool& any_s16, int sh16 = kSH16F) {
+                         std::vector<StripRow>& rows, bool& any_s16, int sh16 = kSH16F, bool force32 = false) {
 	rows.clear();
 	any_s16 = false;
 	// rows [a, b) of the partition free of non-ACGT bytes?  (64-row granularity, conservative)
@@ -499,7 +500,7 @@ static void build_strips(b200_handle* h, const b200_partition* p, int m, const s
 	};
 	// the packed kernel may be used for a strip iff the caller allows it and the strip's ROWS are pure A/C/G/T
 	// (non-ACGT COLUMN bytes are exact in the packed kernel: they mismatch every A/C/G/T row)
-	const bool allow16 = (h->cfg.kernel == B200_KERNEL_AUTO || h->cfg.kernel == B200_KERNEL_S16X2);
+	const bool allow16 = !force32 && (h->cfg.kernel == B200_KERNEL_AUTO || h->cfg.kernel == B200_KERNEL_S16X2);
 	size_t next_sr = 0;
 	int r = 0;
 	while (r < m) {
@@ -553,30 +554,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		special_row_ids(total_rows, bh, p->special_row_interval, all_ids);
 		for (int g : all_ids) if (g > row_offset && g <= row_offset + m) sr_ids.push_back(g - row_offset);
 	}
-	std::vector<StripRow> srows;
-	bool any_s16 = false;
-	build_strips(h, p, m, sr_ids, srows, any_s16);
-	h->hjobs.clear();
-	for (const StripRow& sr : srows) {
-		StripJob j;
-		memset(&j, 0, sizeof(j));
-		j.i0 = sr.i0; j.rows = sr.rows; j.j0 = p->j0; j.cols = n;
-		j.dep = (int)h->hjobs.size() - 1;
-		j.flags = sr.flags | (p->first_col_init == B200_INIT_ZEROES ? JOB_LEFT_ZERO : 0);
-		j.left_off = sr.left_off;
-		j.right_off = p->want_last_column ? sr.left_off : -1;
-		j.sra_off = sr.sra_row >= 0 ? (long long)sr.sra_row * n : -1;
-		j.sra_index = sr.sra_row;
-		h->hjobs.push_back(j);
-	}
-	const int njobs = (int)h->hjobs.size();
-	if (!any_s16) kind = B200_KERNEL_S32;
-
 	// ---- buffers
-	CU(h, h->jobs.reserve(njobs));
-	CU(h, h->progress.reserve(njobs));
-	CU(h, h->results.reserve(njobs));
-	CU(h, h->hresults.reserve(njobs));
 	if (!sr_ids.empty()) CU(h, h->sra.reserve(sr_ids.size() * (size_t)n));
 	if (p->want_last_column) CU(h, h->right.reserve((size_t)m + 1));
 	const bool have_cb = cb != nullptr;
@@ -586,8 +564,12 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		CU(h, h->hcells.reserve(stage_cells));
 	}
 	if (reset_scalars(h, sw ? 0 : -kInf)) return 1;
-	CU(h, cudaMemcpyAsync(h->jobs.p, h->hjobs.data(), njobs * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
-	CU(h, cudaMemsetAsync(h->progress.p, 0, njobs * sizeof(int), h->stream));
+
+	// The packed kernel keeps scores in a 16-bit frame: -INF E/F inputs vanish after one cell exactly as in the reference,
+	// but an NW partition whose border carries -INF in H (it can, when the border comes from a pruned neighbour) must
+	// drift like the reference's plain int32 arithmetic does -> such partitions run the int32 kernel.
+	bool force32 = false;
+	auto has_minf_h = [](const Cell* c, size_t len) { for (size_t k = 0; k < len; k++) if (c[k].h <= -kInf / 2) return true; return false; };
 
 	// ---- first row -> busH[j0..j1), first column -> left[0..m]   (AbstractDiagonalAligner.cpp:83-89,409-456)
 	Cell corner_col; corner_col.h = 0; corner_col.x = -kInf;
@@ -606,6 +588,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	} else {
 		cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p), n);
 		first_row_tail = h->hcells.p[n - 1];
+		if (!sw && has_minf_h(h->hcells.p, (size_t)n)) force32 = true;
 		CU(h, cudaMemcpyAsync(h->busH.p + p->j0, h->hcells.p, (size_t)n * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 		CU(h, cudaStreamSynchronize(h->stream));
 	}
@@ -615,6 +598,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			h->hcells.p[0] = corner_col;
 			cb->receive_first_column(cb->ctx, reinterpret_cast<b200_cell*>(h->hcells.p + 1), m);
 			h->cont_corner = h->hcells.p[m];
+			if (!sw && has_minf_h(h->hcells.p, (size_t)m + 1)) force32 = true;
 			CU(h, cudaMemcpyAsync(h->left.p, h->hcells.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 			CU(h, cudaStreamSynchronize(h->stream));
 		} else {
@@ -623,6 +607,34 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			h->stat_launches++;
 		}
 	}
+
+	// ---- strips (after the borders: their content can force the int32 kernel, whose strips are 512 rows)
+	if (cont && h->cont_force32) force32 = true;                 // a chunked partition keeps the kernel of its first chunk
+	h->cont_force32 = force32;
+	std::vector<StripRow> srows;
+	bool any_s16 = false;
+	build_strips(h, p, m, sr_ids, srows, any_s16, kSH16F, force32);
+	h->hjobs.clear();
+	for (const StripRow& sr : srows) {
+		StripJob j;
+		memset(&j, 0, sizeof(j));
+		j.i0 = sr.i0; j.rows = sr.rows; j.j0 = p->j0; j.cols = n;
+		j.dep = (int)h->hjobs.size() - 1;
+		j.flags = sr.flags | (p->first_col_init == B200_INIT_ZEROES ? JOB_LEFT_ZERO : 0);
+		j.left_off = sr.left_off;
+		j.right_off = p->want_last_column ? sr.left_off : -1;
+		j.sra_off = sr.sra_row >= 0 ? (long long)sr.sra_row * n : -1;
+		j.sra_index = sr.sra_row;
+		h->hjobs.push_back(j);
+	}
+	const int njobs = (int)h->hjobs.size();
+	if (!any_s16) kind = B200_KERNEL_S32;
+	CU(h, h->jobs.reserve(njobs));
+	CU(h, h->progress.reserve(njobs));
+	CU(h, h->results.reserve(njobs));
+	CU(h, h->hresults.reserve(njobs));
+	CU(h, cudaMemcpyAsync(h->jobs.p, h->hjobs.data(), njobs * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
+	CU(h, cudaMemsetAsync(h->progress.p, 0, njobs * sizeof(int), h->stream));
 
 	static const bool dbg = getenv("B200_DEBUG") != nullptr;
 	if (dbg) fprintf(stderr, "[b200] launch: %d strips, prune=%d track=%d kind=%d\n", njobs, (int)(p->prune && sw), track, kind);
@@ -1180,6 +1192,9 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 	if (custom_row) {
 		cb->receive_first_row(cb->ctx, reinterpret_cast<b200_cell*>(h0->mg.hrow.p), n);
 		first_row_tail = h0->mg.hrow.p[n - 1];
+		if (!sw && kind == B200_KERNEL_S16X2)
+			for (int k = 0; k < n; k++)
+				if (h0->mg.hrow.p[k].h <= -kInf / 2) FAIL("chained alignment: NW border with -INF in H needs the int32 kernel (create the handles with B200_KERNEL_S32)");
 	} else {
 		const int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
 		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * n - (type == B200_INIT_GAPS ? kGapOpen : 0);

@@ -201,3 +201,30 @@ def test_packed_and_byte_sequences_agree(b200, monkeypatch, m, n):
         o2 = O.full_matrix(a[17 % m:], b[3 % n:], O.SW, row_ids=[m - 17 % m - 1])
         assert r["best"] == (o2["best"][0], o2["best"][1] + 17 % m, o2["best"][2] + 3 % n)
         al.close()
+
+
+def test_nw_border_with_minus_inf_routes_to_int32(b200):
+    """An NW partition whose first column / first row carries -INF in H (borders handed over by a pruned neighbour): the
+    16-bit frame of the packed kernel cannot drift like the reference's plain int32 arithmetic, so the engine must run
+    such a partition on the int32 kernel by itself -- also when the handle asks for the packed one."""
+    a, b = _pair(3000, 2600, 41)
+    i0, j0, i1, j1 = 100, 200, 2900, 2500
+    rng = np.random.default_rng(7)
+    fr = np.zeros(j1 - j0 + 1, O.CELL); fc = np.zeros(i1 - i0 + 1, O.CELL)
+    fr["h"] = -np.cumsum(rng.integers(0, 4, fr.size)); fr["x"] = fr["h"] - rng.integers(1, 9, fr.size)
+    fc["h"] = -np.cumsum(rng.integers(0, 4, fc.size)); fc["x"] = fc["h"] - rng.integers(1, 9, fc.size)
+    fc[0] = fr[0]
+    fc["h"][700:1500] = -O.INF; fc["x"][700:1500] = -O.INF
+    fr["h"][1000:1300] = -O.INF; fr["x"][1000:1300] = -O.INF
+    o = O.full_matrix(a[i0:i1], b[j0:j1], O.NW, first_row=fr, first_row_type=O.INIT_CUSTOM, first_col=fc,
+                      first_col_type=O.INIT_CUSTOM, row_ids=[i1 - i0 - 1])
+    for kernel in (b200.KERNEL_S16X2, b200.KERNEL_AUTO):
+        al = b200.Aligner(kernel=kernel)
+        al.set_sequences(a, b)
+        r = al.align_partition(i0, j0, i1, j1, recurrence=b200.NEEDLEMAN_WUNSCH, first_row_init=b200.INIT_CUSTOM,
+                               first_col_init=b200.INIT_CUSTOM, first_row=fr, first_col=fc, want_last_row=True,
+                               want_last_column=True, want_best_score=False)
+        assert r["kernel_used"] == b200.KERNEL_S32
+        assert np.array_equal(r["rows"][i1], o["rows"][i1 - i0 - 1])
+        assert np.array_equal(r["last_column"], o["last_col"])
+        al.close()
