@@ -283,19 +283,21 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 	sp.opt = strip_opt();
 	const bool sw = recurrence == B200_SMITH_WATERMAN;
 	const void* fn = nullptr;
-	if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F && h->ov.mixed) {
-		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16F, true, true, true> : (const void*)strip_kernel_s16<kR16F, true, false, true>;
-		else    fn = track ? (const void*)strip_kernel_s16<kR16F, false, true, true> : (const void*)strip_kernel_s16<kR16F, false, false, true>;
-	} else if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F) {
-		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16F, true, true> : (const void*)strip_kernel_s16<kR16F, true, false>;
-		else    fn = track ? (const void*)strip_kernel_s16<kR16F, false, true> : (const void*)strip_kernel_s16<kR16F, false, false>;
-	} else if (kernel_kind == B200_KERNEL_S16X2) {
-		if (sw) fn = track ? (const void*)strip_kernel_s16<kR16, true, true> : (const void*)strip_kernel_s16<kR16, true, false>;
-		else    fn = track ? (const void*)strip_kernel_s16<kR16, false, true> : (const void*)strip_kernel_s16<kR16, false, false>;
-	} else {
+	const bool chain = sp.chain.enabled != 0;
+	// packed kernel <rows per virtual lane, SW, TRACK, MIXED, CHAIN>: every combination in use is its own instance
+#define S16_PICK(R, MIXED)                                                                                                   \
+	(chain ? (sw ? (track ? (const void*)strip_kernel_s16<R, true, true, MIXED, true> : (const void*)strip_kernel_s16<R, true, false, MIXED, true>)    \
+	             : (track ? (const void*)strip_kernel_s16<R, false, true, MIXED, true> : (const void*)strip_kernel_s16<R, false, false, MIXED, true>)) \
+	       : (sw ? (track ? (const void*)strip_kernel_s16<R, true, true, MIXED, false> : (const void*)strip_kernel_s16<R, true, false, MIXED, false>)  \
+	             : (track ? (const void*)strip_kernel_s16<R, false, true, MIXED, false> : (const void*)strip_kernel_s16<R, false, false, MIXED, false>)))
+	if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F && h->ov.mixed) fn = S16_PICK(kR16F, true);
+	else if (kernel_kind == B200_KERNEL_S16X2 && SH == kSH16F) fn = S16_PICK(kR16F, false);
+	else if (kernel_kind == B200_KERNEL_S16X2) fn = S16_PICK(kR16, false);
+	else {
 		if (sw) fn = track ? (const void*)strip_kernel_s32<kR32, true, true> : (const void*)strip_kernel_s32<kR32, true, false>;
 		else    fn = track ? (const void*)strip_kernel_s32<kR32, false, true> : (const void*)strip_kernel_s32<kR32, false, false>;
 	}
+#undef S16_PICK
 	int grid = grid_for(h, fn, njobs, chained);
 	h->last_grid_warps = grid * kWarpsPerBlock;
 	void* args[] = {(void*)&sp};
@@ -639,7 +641,9 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	static const bool dbg = getenv("B200_DEBUG") != nullptr;
 	if (dbg) fprintf(stderr, "[b200] launch: %d strips, prune=%d track=%d kind=%d\n", njobs, (int)(p->prune && sw), track, kind);
 	// ---- the alignment itself: one persistent launch
-	h->ov.prune = (p->prune && sw && track == 2 && kind == B200_KERNEL_S16X2) ? 1 : 0;
+	// block pruning: SW stage 1 behind a zero first column, as in the reference (sw_stage1.cpp:219-225); a partition that
+	// starts from a real left border is pruned only by the chain instances, which carry that border in the pruning test
+	h->ov.prune = (p->prune && sw && track == 2 && kind == B200_KERNEL_S16X2 && p->first_col_init == B200_INIT_ZEROES) ? 1 : 0;
 	h->ov.prune_i1 = p->super_i1 > 0 ? p->super_i1 : p->i1;
 	h->ov.prune_j1 = p->super_j1 > 0 ? p->super_j1 : p->j1;
 	// special rows are streamed out while the kernel runs: host-mapped completion flags, one per row

@@ -315,10 +315,17 @@ __device__ __forceinline__ void chain_notify_right(const StripParams& p, int job
 	chain_notify_right_(p.chain.chunks, p.chain.nx_events, p.chain.nx_queue, p.chain.nx_tail, p.chain.nstrips, p.chain.nchunks_total, p.chain.world, job, p.trace, p.nx_trace);
 }
 
+// CHAIN is a compile-time property of the packed kernel: the single-GPU instances carry none of the chain's code or
+// registers (measured on a 4.6M x 5M pair, profiles/r02_single_gpu_ab.txt: the run-time switch alone cost 10 % with
+// pruning and 1 % without, the per-segment statistics and the left-border term of the pruning test 2 % each -- the
+// kernel sits at the 128-register limit).  The int32 kernel takes the switch at run time (CHAIN < 0).
+template <int CHAIN>
+__device__ __forceinline__ bool chain_on(const StripParams& p) { return CHAIN < 0 ? p.chain.enabled != 0 : CHAIN != 0; }
 // next job of this launch, or -1 (all lanes return the same value)
+template <int CHAIN>
 __device__ __forceinline__ int claim_job(const StripParams& p, int lane) {
 	int job;
-	if (p.chain.enabled) job = chain_pop(p, lane);
+	if (chain_on<CHAIN>(p)) job = chain_pop(p, lane);
 	else {
 		job = 0;
 		if (lane == 0) job = atomicAdd(p.job_counter, 1);
@@ -335,10 +342,11 @@ __device__ __forceinline__ int claim_job(const StripParams& p, int lane) {
 
 // Resolve job id -> JobCtx.  Outside chain mode the job table is explicit; in chain mode job = k * S + r and the
 // geometry comes from the strip and chunk tables.
+template <int CHAIN>
 __device__ __forceinline__ JobCtx fetch_job(const StripParams& p, int job) {
 	JobCtx c;
 	c.job = job;
-	if (!p.chain.enabled) {
+	if (!chain_on<CHAIN>(p)) {
 		c.jb = p.jobs[job];
 		c.pidx = job; c.prog_base = 0;
 		return c;
@@ -363,9 +371,10 @@ __device__ __forceinline__ JobCtx fetch_job(const StripParams& p, int job) {
 }
 // Chain mode keeps ONE result per strip: the jobs of a strip run strictly one after the other (chunk c+1 starts from
 // the border that chunk c delivers at its very end), so each job folds the strip's previous best into its own.
+template <int CHAIN>
 __device__ __forceinline__ void store_result(const StripParams& p, const JobCtx& c, int bs, int bi, int bj) {
 	Score3 o; o.score = bs == INT_MIN ? -kInf : bs; o.i = bi; o.j = bj; o.pad = 0;
-	if (p.chain.enabled && c.job >= p.chain.nstrips) {
+	if (chain_on<CHAIN>(p) && c.job >= p.chain.nstrips) {
 		// written by another SM: read through L2 (the causality chain is (r,k-1) result -> fence -> left event -> ... -> our pop)
 		const int4 q = __ldcg(reinterpret_cast<const int4*>(p.results + c.pidx));
 		if (q.y >= 0 && (o.i < 0 || better(q.x, q.y, q.z, o.score, o.i, o.j))) { o.score = q.x; o.i = q.y; o.j = q.z; }

@@ -293,9 +293,9 @@ struct StripS16 {
 		s.blk = 0x80008000u;
 	}
 
-	template <bool PARTIAL>
+	template <bool PARTIAL, bool CHAIN>
 	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane, unsigned lut_addr = 0) {
-		const JobCtx cx = fetch_job(p, job);
+		const JobCtx cx = fetch_job<CHAIN ? 1 : 0>(p, job);
 		const StripJob& jb = cx.jb;
 		const int rows = jb.rows, cols = jb.cols, i0 = jb.i0, j0 = jb.j0;
 		const int rb_lo = (2 * lane) * R, rb_hi = (2 * lane + 1) * R;     // first row of each half inside the strip
@@ -354,13 +354,13 @@ struct StripS16 {
 		int seen = jb.dep < 0 ? INT_MAX : 0;   // progress (in our columns) of the strip above observed by our last acquire (OPT_SEEN_CACHE)
 		const int opt = p.opt;
 		int pos = 0;                           // next column to decide in skip mode
-		const bool chained = p.chain.enabled != 0;   // chain mode: our first publication lets the strip below start
+		constexpr bool chained = CHAIN;              // chain mode: our first publication lets the strip below start
 		// A job that starts from a real left border (custom first column, or the border delivered by the chunk on our left
 		// in chain mode) must carry that border in the pruning test until every virtual lane has consumed its cells: the
 		// running block maxima only know the lanes that have started (the alignment path may enter through the lower rows).
 		int lpend = INT_MIN;
 		bool left_dead = false;
-		if (prune && !lz) {
+		if (CHAIN && prune && !lz) {                // (the single-GPU instances prune only behind a zero first column: engine.cu)
 			lpend = __reduce_max_sync(0xffffffffu, lmaxv);
 			if (lpend < 0) lpend = 0;
 			const int g = ld_uniform(p.global_best);
@@ -447,8 +447,9 @@ struct StripS16 {
 			// =========================== COMPUTE mode: one segment [c0, c1) ===========================
 			const int c0 = pos;
 			int c1 = cols;
-			const unsigned long long seg_t0 = global_ns();     // statistics: time this warp spends in compute segments
-			if (chained && p.sm_load != nullptr && lane == 0) { atomicAdd(p.sm_load, 1); atomicAdd(p.sm_load + 1 + sched_slot(), 1); }
+			unsigned long long seg_t0 = 0;                     // statistics (chain instances): time this warp spends in compute segments
+			if (CHAIN) seg_t0 = global_ns();
+			if (CHAIN && p.sm_load != nullptr && lane == 0) { atomicAdd(p.sm_load, 1); atomicAdd(p.sm_load + 1 + sched_slot(), 1); }
 #pragma unroll 1
 			for (int tb = c0; tb < c1 + V - 1; tb += 32) {
 				// ---- re-centre the frame on H(row 0 of the strip, last column done by virtual lane 0)
@@ -578,9 +579,9 @@ struct StripS16 {
 				}
 			}
 			computed_cols += c1 - c0;
-			if (lane == 0) {
+			if (CHAIN && lane == 0) {
 				atomicAdd(p.cells_done + 1, global_ns() - seg_t0);
-				if (chained && p.sm_load != nullptr) { atomicSub(p.sm_load, 1); atomicSub(p.sm_load + 1 + sched_slot(), 1); }
+				if (p.sm_load != nullptr) { atomicSub(p.sm_load, 1); atomicSub(p.sm_load + 1 + sched_slot(), 1); }
 			}
 			if (c1 >= cols) {
 				// the segment ran to the last column: every half froze when it passed it, so the registers hold column cols-1
@@ -616,11 +617,11 @@ struct StripS16 {
 				if (better(os, oi, oj, bs, bi, bj)) { bs = os; bi = oi; bj = oj; }
 			}
 			if (lane == 0) {
-				store_result(p, cx, bs, bi, bj);
+				store_result<CHAIN ? 1 : 0>(p, cx, bs, bi, bj);
 				if (bs != INT_MIN) push_best(p, bs);
 			}
 		}
-		if (p.chain.enabled) {
+		if (CHAIN) {
 			// the right border is in the next GPU's memory and our best is folded into the strip's result: hand the strip over
 			__syncwarp();
 			if (lane == 0) chain_notify_right(p, job);
@@ -632,7 +633,7 @@ struct StripS16 {
 
 // MIXED: the launch also contains JOB_S32 strips (rows with N / IUPAC bytes) and columns may hold such bytes: PRMT
 // variant plus the int32 path.  Pure A/C/G/T launches of the whole-partition instance (R = kR16F) use the LUT variant.
-template <int R, bool SW, bool TRACK, bool MIXED = false>
+template <int R, bool SW, bool TRACK, bool MIXED = false, bool CHAIN = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) strip_kernel_s16(const StripParams p) {
 	constexpr bool LUT = !MIXED;
 	using K = StripS16<R, SW, TRACK, LUT>;
@@ -654,11 +655,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) strip_kernel_s16(const
 		lut_addr = (unsigned)__cvta_generic_to_shared(lut);
 	}
 	for (;;) {
-		const int job = claim_job(p, lane);
+		const int job = claim_job<CHAIN ? 1 : 0>(p, lane);
 		if (job < 0) break;
 		if (ld_uniform(p.stop_flag)) break;
 		int flags, rows;
-		if (p.chain.enabled) { const StripRow& sr = p.chain.strips[job % p.chain.nstrips]; flags = sr.flags; rows = sr.rows; }
+		if (CHAIN) { const StripRow& sr = p.chain.strips[job % p.chain.nstrips]; flags = sr.flags; rows = sr.rows; }
 		else { flags = p.jobs[job].flags; rows = p.jobs[job].rows; }
 		if (flags & JOB_PRUNED) {
 			// diag path only. Same semantics as the int32 kernel: -INF to the right border, no score (CUDAligner.cu:950-960)
@@ -671,8 +672,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) strip_kernel_s16(const
 			continue;
 		}
 		if (MIXED && (flags & JOB_S32)) K32::run_job(p, job, smu[warp].s32, warp, lane);      // rows with N / IUPAC bytes: exact int32 path
-		else if (rows < K::SH) K::template run_job<true>(p, job, sm, warp, lane, lut_addr);
-		else K::template run_job<false>(p, job, sm, warp, lane, lut_addr);
+		else if (rows < K::SH) K::template run_job<true, CHAIN>(p, job, sm, warp, lane, lut_addr);
+		else K::template run_job<false, CHAIN>(p, job, sm, warp, lane, lut_addr);
 	}
 }
 

@@ -27,7 +27,7 @@ struct StripS32 {
 	};
 
 	__device__ static void run_job(const StripParams& p, int job, Smem& sm, int warp, int lane) {
-		const JobCtx cx = fetch_job(p, job);
+		const JobCtx cx = fetch_job<-1>(p, job);
 		const StripJob& jb = cx.jb;
 		const int rows = jb.rows, cols = jb.cols, i0 = jb.i0, j0 = jb.j0;
 
@@ -182,7 +182,7 @@ struct StripS32 {
 				if (better(os, oi, oj, bs, bi, bj)) { bs = os; bi = oi; bj = oj; }
 			}
 			if (lane == 0) {
-				store_result(p, cx, bs, bi, bj);
+				store_result<-1>(p, cx, bs, bi, bj);
 				if (bs != INT_MIN) push_best(p, bs);
 			}
 		}
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) strip_kernel_s32(const St
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	typename K::Smem& sm = smw[warp];
 	for (;;) {
-		const int job = claim_job(p, lane);
+		const int job = claim_job<-1>(p, lane);
 		if (job < 0) break;
 		if (ld_uniform(p.stop_flag)) break;
 		K::run_job(p, job, sm, warp, lane);
