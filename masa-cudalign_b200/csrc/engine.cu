@@ -1144,10 +1144,10 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 	std::vector<int> sr_ids;
 	if (p->want_special_rows) special_row_ids(m, bh, p->special_row_interval, sr_ids);
 	// Strip height of the packed kernel: 1024 rows (16 per virtual lane) is the cheapest per cell, but a front needs about
-	// 2400 resident strips per GPU to fill it; when the rows cannot provide that many per GPU, 512-row strips (8 per
+	// 2400 resident strips per GPU to fill it (148 SMs x 16 warps); when the rows cannot provide that many per GPU, 512-row strips (8 per
 	// virtual lane) double the number of strips and halve the dependent chain of a step.  B200_CHAIN_SH overrides.
 	int sh16 = kSH16F;
-	if (h0->acgt_only && (long long)m / kSH16F < 1600LL * world) sh16 = kSH16;
+	if (h0->acgt_only && (long long)m / kSH16F < 2400LL * world) sh16 = kSH16;      // fewer 1024-row strips than resident warps
 	if (const char* e = getenv("B200_CHAIN_SH")) sh16 = atoi(e) == kSH16 ? kSH16 : kSH16F;
 	if (!h0->acgt_only) sh16 = kSH16F;
 	std::vector<StripRow> srows;

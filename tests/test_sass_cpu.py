@@ -2,7 +2,7 @@
 
 `cuobjdump -sass` of libb200align.so is inspected with tools/sass_step_count.py: the steady wavefront loop of the
 production kernel must be built from the packed DPX instructions (VIADDMNMX.S16x2 / VIMNMX3.S16x2), must stay inside
-the instruction budget the roofline in profiles/r01_inst_per_cell.json is computed from, and must not spill inside the
+the instruction budget the roofline in profiles/r02_inst_per_cell.json is computed from, and must not spill inside the
 loop.  A compiler or source change that silently adds 10 % to the step shows up here, before any GPU time is spent."""
 import json
 import os
@@ -50,7 +50,7 @@ def test_steady_loop_instruction_budget():
     assert best["ops"].get("LDS", 0) <= 17.0                               # 16 LUT reads + lane 0's top-border LDS.128
     assert best["ops"].get("SHFL", 0) == 3.0
     assert "LDL" not in best["ops"] and "STL" not in best["ops"], "spill inside the steady loop"
-    with open(os.path.join(ROOT, "profiles", "r01_inst_per_cell.json")) as f:
+    with open(os.path.join(ROOT, "profiles", "r02_inst_per_cell.json")) as f:
         budget = json.load(f)["s16x2"]
     assert best["per_cell"] <= budget * 1.03, (best["per_cell"], budget)   # the roofline denominator stays honest
     # the exact-maximum variant (used while the best score is < 128) costs the 8 extra VIMNMX3
