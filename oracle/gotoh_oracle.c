@@ -215,3 +215,100 @@ int go_largest_partition(const go_xpoint* pts, int n) {                 /* Cross
     }
     return mi > mj ? mi : mj;
 }
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Stage 5 (C/stage5/sw_stage5.cpp:86-319): traceback of one stage-4 partition.  Full (H, E, F) tables of the
+ * partition [a, b) with the border rules of :134-143 (NB: stage 5 names the VERTICAL gap state e and the
+ * horizontal one f, :154-155), then the walk of :209-305 from the bottom-right corner:
+ *   state MATCH: diagonal first, then vertical (e), then horizontal (f)  (:222-241)
+ *   state GAP_2: forced vertical step, GAP_1: forced horizontal step     (:242-257)
+ *   a gap step returns to MATCH when the gap was opened in that cell (e == h_above - first / f == h_left - first)
+ *   leftovers: vertical steps while i > 0, then horizontal steps while j > 0 (:291-308)
+ * An end crosspoint of type MATCH makes the reference add one extra row and column (:117-120) that the walk
+ * leaves immediately (:197-200) without looking at them; they are not computed here.
+ * ops[k] = direction of step k (0 diagonal, 1 vertical = gap in seq1, 2 horizontal = gap in seq0), in walk order;
+ * at most (b.i-a.i)+(b.j-a.j) steps.  st accumulates exactly like total_score_t (:51-67). */
+int go_stage5_partition(const unsigned char* seq0, const unsigned char* seq1, go_xpoint a, go_xpoint b,
+                        unsigned char* ops, go_s5_stats* st) {
+    const int first = GAP_OPEN + GAP_EXT;
+    int di = b.i - a.i, dj = b.j - a.j, n = 0;
+    if (di < 0 || dj < 0) return -1;
+    if (di == 0) {                                           /* :88-99: pure horizontal run */
+        int sum = -dj * GAP_EXT;
+        if (a.type != T_GAP_1) { st->gap_open++; sum -= GAP_OPEN; }
+        for (int j = 0; j < dj; j++) { ops[n++] = 2; st->gap_ext++; }
+        st->score += sum;
+        return n;
+    }
+    if (dj == 0) {                                           /* :100-112: pure vertical run */
+        int sum = -di * GAP_EXT;
+        if (a.type != T_GAP_2) { st->gap_open++; sum -= GAP_OPEN; }
+        for (int i = 0; i < di; i++) { ops[n++] = 1; st->gap_ext++; }
+        st->score += sum;
+        return n;
+    }
+    const size_t W = (size_t)dj + 1;
+    int* H = (int*)malloc(sizeof(int) * W * ((size_t)di + 1));
+    int* E = (int*)malloc(sizeof(int) * W * ((size_t)di + 1));
+    int* F = (int*)malloc(sizeof(int) * W * ((size_t)di + 1));
+    const unsigned char* s0 = seq0 + a.i;
+    const unsigned char* s1 = seq1 + a.j;
+    for (int j = 1; j <= dj; j++) { H[j] = -j * GAP_EXT - GAP_OPEN * (a.type != T_GAP_1); E[j] = -GO_INF; F[j] = -GO_INF; }
+    H[0] = a.type != T_MATCH ? -GO_INF : 0;
+    E[0] = -GO_INF; F[0] = -GO_INF;
+    for (int i = 1; i <= di; i++) {
+        int* h0 = H + W * i; int* h1 = h0 - W; int* e0 = E + W * i; int* e1 = e0 - W; int* f0 = F + W * i;
+        h0[0] = -i * GAP_EXT - GAP_OPEN * (a.type != T_GAP_2);
+        f0[0] = -GO_INF; e0[0] = -GO_INF;
+        for (int j = 1; j <= dj; j++) {
+            e0[j] = MAX2(h1[j] - first, e1[j] - GAP_EXT);
+            f0[j] = MAX2(h0[j - 1] - first, f0[j - 1] - GAP_EXT);
+            int d = h1[j - 1] + (s0[i - 1] == s1[j - 1] ? MATCH : MISMATCH);
+            h0[j] = MAX2(d, MAX2(e0[j], f0[j]));
+        }
+    }
+    int i = di, j = dj, c = b.type, sum = 0;
+    while (i > 0 && j > 0) {
+        const int hh = H[W * i + j], ee = E[W * i + j], ff = F[W * i + j];
+        const int same = s0[i - 1] == s1[j - 1];
+        int dir;
+        if (c == T_MATCH) {
+            if (hh == H[W * (i - 1) + j - 1] + (same ? MATCH : MISMATCH)) dir = 0;
+            else if (hh == ee) dir = 1;
+            else dir = 2;                                   /* hh == ff: H is the maximum of the three */
+        } else dir = (c == T_GAP_2) ? 1 : 2;
+        if (dir == 1) c = (ee == H[W * (i - 1) + j] - first) ? T_MATCH : T_GAP_2;
+        else if (dir == 2) c = (ff == H[W * i + j - 1] - first) ? T_MATCH : T_GAP_1;
+        else c = T_MATCH;
+        ops[n++] = (unsigned char)dir;
+        if (dir == 0) {
+            if (same) { st->matches++; sum += MATCH; } else { st->mismatches++; sum += MISMATCH; }
+            i--; j--;
+        } else {
+            st->gap_ext++;
+            if (c == T_MATCH) { st->gap_open++; sum -= first; } else sum -= GAP_EXT;
+            if (dir == 1) i--; else j--;
+        }
+    }
+    for (; i > 0; i--) { ops[n++] = 1; st->gap_ext++; c = T_GAP_2; sum -= GAP_EXT; }
+    for (; j > 0; j--) { ops[n++] = 2; st->gap_ext++; c = T_GAP_1; sum -= GAP_EXT; }
+    if (a.type == T_MATCH && c != T_MATCH) sum -= GAP_OPEN;  /* :309-311: the opening is charged, not counted */
+    st->score += sum;
+    free(H); free(E); free(F);
+    return n;
+}
+
+/* stage5() driver loop, :404-424: all partitions in order.  op_len[k] (k = 1..n-1) = steps of partition (k-1, k), written
+ * at ops + (pts[k-1].i - pts[0].i) + (pts[k-1].j - pts[0].j).  Returns 0, or -1 on bad input. */
+int go_stage5(const unsigned char* seq0, const unsigned char* seq1, const go_xpoint* pts, int n, unsigned char* ops,
+              int* op_len, go_s5_stats* st) {
+    memset(st, 0, sizeof(*st));
+    if (n > 0) op_len[0] = 0;
+    for (int k = 1; k < n; k++) {
+        long long off = (long long)(pts[k - 1].i - pts[0].i) + (pts[k - 1].j - pts[0].j);
+        int r = go_stage5_partition(seq0, seq1, pts[k - 1], pts[k], ops + off, st);
+        if (r < 0) return -1;
+        op_len[k] = r;
+    }
+    return 0;
+}

@@ -42,6 +42,15 @@ int go_stage4_split_one(const unsigned char* seq0, const unsigned char* seq1, go
 int go_stage4_round(const unsigned char* seq0, const unsigned char* seq1, const go_xpoint* in, int n, int max_part, go_xpoint* out, int* changed);
 int go_largest_partition(const go_xpoint* pts, int n);
 
+/* Stage 5 (C/stage5/sw_stage5.cpp:86-319): traceback of the partitions between consecutive stage-4 crosspoints.
+ * go_s5_stats == total_score_t (:51-67).  ops: one byte per step in walk order (bottom-right -> top-left of each partition),
+ * 0 = diagonal, 1 = vertical (the reference's dot(...,1): gap in seq1), 2 = horizontal (dot(...,2): gap in seq0). */
+typedef struct { int score, matches, mismatches, gap_open, gap_ext; } go_s5_stats;
+int go_stage5_partition(const unsigned char* seq0, const unsigned char* seq1, go_xpoint a, go_xpoint b,
+                        unsigned char* ops, go_s5_stats* st);
+int go_stage5(const unsigned char* seq0, const unsigned char* seq1, const go_xpoint* pts, int n, unsigned char* ops,
+              int* op_len, go_s5_stats* st);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,3 +138,61 @@ def stage4(s0, s1, points, max_part=16):
 def golden_points(entries):
     """[(type, i, j, score), ...] as stored in tests/golden -> XPOINT array."""
     return np.array([(i, j, t, s) for (t, i, j, s) in entries], dtype=XPOINT)
+
+
+class GoS5Stats(C.Structure):
+    _fields_ = [("score", C.c_int), ("matches", C.c_int), ("mismatches", C.c_int), ("gap_open", C.c_int), ("gap_ext", C.c_int)]
+
+
+def stage5(s0, s1, points):
+    """The reference's stage-5 traceback (C restatement go_stage5) over the partitions between consecutive crosspoints.
+    Returns (ops, op_off, op_len, stats): partition k (between points k-1 and k) owns ops[op_off[k] : op_off[k] + op_len[k]],
+    one byte per step from its bottom-right corner (0 diagonal, 1 vertical = gap in seq1, 2 horizontal = gap in seq0)."""
+    L = lib()
+    L.go_stage5.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(GoS5Stats)]
+    a = np.ascontiguousarray(s0, dtype=np.uint8); b = np.ascontiguousarray(s1, dtype=np.uint8)
+    pts = np.ascontiguousarray(points, dtype=XPOINT)
+    cap = int(pts["i"][-1] - pts["i"][0]) + int(pts["j"][-1] - pts["j"][0])
+    ops = np.full(cap + 1, 255, np.uint8)
+    op_len = np.zeros(pts.size, np.int32)
+    st = GoS5Stats()
+    rc = L.go_stage5(a.ctypes.data, b.ctypes.data, pts.ctypes.data, pts.size, ops.ctypes.data, op_len.ctypes.data, C.byref(st))
+    assert rc == 0, f"stage-5 oracle failed with {rc}"
+    return ops[:cap], stage5_offsets(pts), op_len, {k: getattr(st, k) for k, _ in GoS5Stats._fields_}
+
+
+def stage5_offsets(points):
+    """op_off[k] = (i[k-1] - i[0]) + (j[k-1] - j[0]): every partition owns as many slots as its longest possible walk."""
+    pts = np.ascontiguousarray(points, dtype=XPOINT)
+    off = np.zeros(pts.size, np.int64)
+    off[1:] = (pts["i"][:-1].astype(np.int64) - int(pts["i"][0])) + (pts["j"][:-1].astype(np.int64) - int(pts["j"][0]))
+    return off
+
+
+def stage5_gaps(points, ops, op_off, op_len):
+    """What stage5() hands to Alignment (dot(), C/stage5/sw_stage5.cpp:70-84, forward sequences; Alignment::addGap run-length
+    merge, C/common/biology/Alignment.cpp, then finalize()'s sort by position): (gaps0, gaps1) as lists of [pos, len].
+    A gap run cut by a crosspoint yields two entries with the same position (the partitions are visited top-down, each one
+    walked bottom-up, so the two halves are not consecutive calls); finalize() orders such twins by the whim of std::sort,
+    so compare the lists sorted by (pos, len)."""
+    pts = np.ascontiguousarray(points, dtype=XPOINT)
+    gaps = ([], [])
+    for k in range(1, pts.size):
+        i, j = int(pts["i"][k] - pts["i"][k - 1]), int(pts["j"][k] - pts["j"][k - 1])
+        i0, j0 = int(pts["i"][k - 1]), int(pts["j"][k - 1])
+        for d in ops[int(op_off[k]):int(op_off[k]) + int(op_len[k])]:
+            if d == 0:
+                i -= 1; j -= 1
+                continue
+            seq, pos = (1, j0 + j + 1) if d == 1 else (0, i0 + i + 1)
+            g = gaps[seq]
+            if g and g[-1][0] == pos:
+                g[-1][1] += 1
+            else:
+                g.append([pos, 1])
+            if d == 1:
+                i -= 1
+            else:
+                j -= 1
+        assert i == 0 and j == 0, f"partition {k}: the walk stopped at ({i},{j})"
+    return sorted(gaps[0]), sorted(gaps[1])

@@ -104,3 +104,30 @@ def test_stage4_restatement_matches_reference(name):
     src = sorted(k for k in g["crosspoints"] if k.startswith("crosspoint_03"))[-1]
     pts = O.stage4(a, b, O.golden_points(g["crosspoints"][src]), 16)
     assert np.array_equal(pts, O.golden_points(g["crosspoints"]["crosspoint_04.00"]))
+
+
+S5_GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "stage5_runs.json")))
+
+
+def s5_pair(name):
+    ge = S5_GOLD[name]["generator"]
+    a, b = synth.make_pair(ge["m"], ge["n"], [tuple(s) for s in ge["segments"]], ge["p_s"], ge["p_d"], ge["p_i"], ge["K"], ge["seed"])
+    assert [hashlib.sha256(a.tobytes()).hexdigest(), hashlib.sha256(b.tobytes()).hexdigest()] == S5_GOLD[name]["seq_sha256"]
+    return a, b
+
+
+@pytest.mark.parametrize("name", sorted(S5_GOLD))
+def test_stage5_restatement_matches_reference(name):
+    """go_stage5 walked over the reference's crosspoint_04 reproduces what the reference's stage 5 stored in
+    alignment.00.bin (read back with the reference's own reader, tests/golden/make_stage5_golden.py): raw score, the
+    four counters of total_score_t and both gap lists."""
+    g = S5_GOLD[name]
+    a, b = s5_pair(name)
+    pts = O.golden_points(g["crosspoint_04"])
+    ops, off, ln, st = O.stage5(a, b, pts)
+    al = g["alignment"]
+    assert st["score"] == al["raw_score"] == int(pts["score"][-1] - pts["score"][0])
+    assert [st[k] for k in ("matches", "mismatches", "gap_open", "gap_ext")] == [al[k] for k in ("matches", "mismatches", "gap_open", "gap_ext")]
+    g0, g1 = O.stage5_gaps(pts, ops, off, ln)
+    assert g0 == sorted(al["gaps0"]) and g1 == sorted(al["gaps1"])
+    assert al["start"] == [int(pts["i"][0]) + 1, int(pts["j"][0]) + 1] and al["end"] == [int(pts["i"][-1]), int(pts["j"][-1])]
