@@ -208,6 +208,20 @@ typedef struct { int i; int j; int type; int score; } b200_xpoint;
 int b200_stage4_round(b200_handle* h, const b200_xpoint* in, int n, int max_partition, b200_xpoint* out);
 int b200_stage4(b200_handle* h, const b200_xpoint* in, int n, int max_partition, b200_xpoint* out, int cap, int* n_out);
 
+/* Stage 5: batched traceback on the GPU (replaces the serial partition loop of C/stage5/sw_stage5.cpp:86-319,404-424:
+ * one CPU thread, static 1024 x 1024 tables).  pts = the stage-4 crosspoints (crosspoint_04.NN); partition k (k = 1..n-1)
+ * lies between pts[k-1] and pts[k].  Every partition is walked back from its bottom-right corner with the reference's
+ * precedence (diagonal, then vertical, then horizontal; :222-257) and leaves one byte per step:
+ *   0 diagonal (match / mismatch), 1 vertical = the reference's dot(..., 1): gap in seq1, 2 horizontal = dot(..., 2): gap in seq0.
+ * Partition k owns the slots ops[off_k .. off_k + op_len[k]) with off_k = (pts[k-1].i - pts[0].i) + (pts[k-1].j - pts[0].j),
+ * so ops needs (pts[n-1].i - pts[0].i) + (pts[n-1].j - pts[0].j) bytes; op_len has n entries (op_len[0] = 0).
+ * Replaying the bytes of partitions 1, 2, ... in order into Alignment::addGapInSeq0/1 (dot(), :70-84) reproduces the
+ * reference's alignment.NN.bin byte for byte (host/stage5_gpu.cpp does exactly that).  *total == total_score_t (:51-67)
+ * summed over all partitions.  Sequences: the ones given to b200_set_sequences (whole sequences, like stage 4). */
+typedef struct { int score, matches, mismatches, gap_open, gap_ext; } b200_s5_stats;
+int b200_stage5(b200_handle* h, const b200_xpoint* pts, int n, unsigned char* ops, long long ops_cap, int* op_len,
+                b200_s5_stats* total);
+
 /* Host-side policy helper (no GPU needed): the special-row ids (rows above, relative to i0) that the reference
  * flushes for a partition of `height` rows: AbstractDiagonalAligner::isSpecialRow,
  * C/libmasa/aligners/AbstractDiagonalAligner.cpp:466-478 (8192-row floor, top and bottom rows excluded).

@@ -51,6 +51,10 @@ class ChainInfo(C.Structure):
                 ("max_strips", C.c_longlong), ("max_jobs", C.c_longlong)]
 
 
+class S5Stats(C.Structure):
+    _fields_ = [("score", C.c_int), ("matches", C.c_int), ("mismatches", C.c_int), ("gap_open", C.c_int), ("gap_ext", C.c_int)]
+
+
 RECV_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int)
 DISP_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_void_p, C.c_int)
 SCORE_FN = C.CFUNCTYPE(None, C.c_void_p, Score)
@@ -71,7 +75,7 @@ EXPORTS = [
     "b200_processed_cells", "b200_kernel_launches", "b200_chain_plan", "b200_mgpu_export", "b200_mgpu_connect", "b200_mgpu_disconnect",
     "b200_last_chain_result", "b200_group_create", "b200_group_destroy", "b200_group_last_error", "b200_group_size", "b200_group_handle",
     "b200_group_set_sequences", "b200_group_align_partition", "b200_group_rank_result",
-    "b200_special_row_ids", "b200_stage4_round", "b200_stage4",
+    "b200_special_row_ids", "b200_stage4_round", "b200_stage4", "b200_stage5",
 ]
 
 _lib = None
@@ -124,6 +128,7 @@ def load_library(path=None):
     lib.b200_special_row_ids.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.b200_stage4_round.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.b200_stage4.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.b200_stage5.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_longlong, C.c_void_p, C.POINTER(S5Stats)]
     if path is None:
         _lib = lib
     return lib
@@ -378,6 +383,20 @@ class Aligner:
         n_out = C.c_int()
         self._check(self.lib.b200_stage4(self.h, pts.ctypes.data, pts.size, max_partition, out.ctypes.data, cap, C.byref(n_out)), "b200_stage4")
         return out[:n_out.value].copy()
+
+    # ---- stage 5 ---------------------------------------------------------------------------------------
+    def stage5(self, points):
+        """Batched traceback of the partitions between consecutive crosspoints.  Returns (ops, op_off, op_len, stats):
+        partition k owns ops[op_off[k] : op_off[k] + op_len[k]], one byte per step from its bottom-right corner."""
+        pts = np.ascontiguousarray(points, dtype=XPOINT)
+        cap = int(pts["i"][-1] - pts["i"][0]) + int(pts["j"][-1] - pts["j"][0])
+        ops = np.full(cap + 1, 255, np.uint8)
+        op_len = np.zeros(pts.size, np.int32)
+        st = S5Stats()
+        self._check(self.lib.b200_stage5(self.h, pts.ctypes.data, pts.size, ops.ctypes.data, cap, op_len.ctypes.data, C.byref(st)), "b200_stage5")
+        off = np.zeros(pts.size, np.int64)
+        off[1:] = (pts["i"][:-1].astype(np.int64) - int(pts["i"][0])) + (pts["j"][:-1].astype(np.int64) - int(pts["j"][0]))
+        return ops[:cap], off, op_len, {k: getattr(st, k) for k, _ in S5Stats._fields_}
 
     def processed_cells(self):
         return self.lib.b200_processed_cells(self.h)
