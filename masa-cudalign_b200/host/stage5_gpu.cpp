@@ -28,7 +28,8 @@ int stage5(Job* job, int id) {
 	ap->printParams(stats);
 	fflush(stats);
 	// the device code has the aligner's compile-time scores (variable_penalties = NOT_SUPPORTED, like the reference GPU aligner)
-	if (ap->getMatch() != 1 || ap->getMismatch() != -3 || ap->getGapOpen() != 3 || ap->getGapExtension() != 2) {
+	// (AlignmentParams keeps the penalties negated: setAffineGapPenalties(-gap_open, -gap_ext), libmasa.cpp:775; :329-330)
+	if (ap->getMatch() != 1 || ap->getMismatch() != -3 || -ap->getGapOpen() != 3 || -ap->getGapExtension() != 2) {
 		fprintf(stderr, "cudalign-b200: stage 5 on the GPU supports the scores +1/-3/3/2 only.\n");
 		exit(1);
 	}
