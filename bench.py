@@ -218,6 +218,20 @@ def workload_name(args, m, n):
             "SW stage-1 with block pruning: best score + end coordinate")
 
 
+def stage_split(path):
+    """Per-stage wall time (ms) from MASA-Core's own GLOBAL STATISTICS block of the work directory (libmasa.cpp timer events:
+    SEQUENCES = FASTA load, STAGE1..STAGE6).  Stages 1-3 run B200Aligner, stage 4 and stage 5 the GPU substitutes."""
+    out = {}
+    try:
+        for line in open(path):
+            f = line.split()
+            if len(f) >= 2 and f[0].endswith(":") and f[0][:-1] in ("SEQUENCES", "INIT", "STAGE1", "STAGE2", "STAGE3", "STAGE4", "STAGE5", "STAGE6", "TOTAL"):
+                out[f[0][:-1].lower()] = float(f[1])
+    except (OSError, ValueError):
+        pass
+    return out
+
+
 def full_alignment_leg(td):
     """Second half of the BASELINE metric: wall time of a complete alignment (stages 1-6) of the config-2 pair (5M x 5M)
     through build/cudalign, the drop-in binary (host/B200Aligner behind MASA-Core's own CLI).  N = 1 only."""
@@ -240,6 +254,7 @@ def full_alignment_leg(td):
         out["stage1_crosspoint"] = open(xp).read().split("\n")[1]
     txt = os.path.join(wd, "alignment.00.txt")
     out["alignment_txt_bytes"] = os.path.getsize(txt) if os.path.exists(txt) else 0
+    out["stage_ms"] = stage_split(os.path.join(wd, "statistics"))
     if p.returncode != 0:
         out["tail"] = p.stdout[-400:]
     return out

@@ -538,6 +538,25 @@ static void build_strips(b200_handle* h, const b200_partition* p, int m, const s
 
 static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition* p, const b200_callbacks* cb, b200_result* out);
 
+// The on-device special-rows area holds every special row of the partition until the host has copied it out (rows are
+// streamed while the kernel runs, but their slots are not recycled).  The reference bounds the NUMBER of rows by
+// --ram-size + --disk-size (C/common/Job.cpp:231-257: interval = rows * 8 * n / budget), so the area is at most that
+// budget; a budget beyond the free HBM is refused here with the numbers instead of a bare cudaMalloc error.
+static int reserve_sra(b200_handle* h, size_t rows, size_t cols) {
+	if (rows == 0) return 0;
+	if (h->sra.reserve(rows * cols) != cudaSuccess) {
+		cudaGetLastError();
+		size_t fr = 0, tot = 0;
+		cudaMemGetInfo(&fr, &tot);
+		char msg[320];
+		snprintf(msg, sizeof(msg), "device special-rows area: %zu rows x %zu columns x 8 B = %.1f GB do not fit into the %.1f GB of free HBM; "
+		         "lower --ram-size/--disk-size (fewer special rows) or split seq1 over more GPUs (--gpus)", rows, cols, rows * cols * 8e-9, fr * 1e-9);
+		h->err = msg;
+		return 1;
+	}
+	return 0;
+}
+
 extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, const b200_callbacks* cb, b200_result* out) {
 	if (!h) return 1;
 	if (!p || !out) { h->err = "b200_align_partition: bad arguments"; return 1; }
@@ -563,7 +582,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		for (int g : all_ids) if (g > row_offset && g <= row_offset + m) sr_ids.push_back(g - row_offset);
 	}
 	// ---- buffers
-	if (!sr_ids.empty()) CU(h, h->sra.reserve(sr_ids.size() * (size_t)n));
+	if (reserve_sra(h, sr_ids.size(), (size_t)n)) return 1;
 	if (p->want_last_column) CU(h, h->right.reserve((size_t)m + 1));
 	const bool have_cb = cb != nullptr;
 	if (have_cb) {
@@ -1222,7 +1241,7 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 		CU(h, h->progress.reserve(S));
 		CU(h, h->results.reserve(S));
 		CU(h, h->hresults.reserve(S));
-		if (!sr_ids.empty()) CU(h, h->sra.reserve(sr_ids.size() * (size_t)std::max<long long>(L.cols, 1)));
+		if (reserve_sra(h, sr_ids.size(), (size_t)std::max<long long>(L.cols, 1))) { h0->err = h->err; return 1; }
 		if (p->want_last_column && h == hlast) CU(h, h->right.reserve((size_t)m + 1));
 		if (reset_scalars(h, INT_MIN)) { h0->err = h->err; return 1; }
 		CU(h, cudaMemcpyAsync(h->mg.strips.p, srows.data(), S * sizeof(StripRow), cudaMemcpyHostToDevice, h->stream));

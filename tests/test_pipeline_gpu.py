@@ -32,6 +32,20 @@ def _run(exe, fa, fb, wd, extra, env=None):
     assert r.returncode == 0, f"{' '.join(cmd)}\n{r.stdout[-3000:]}"
 
 
+_REF_CACHE = {}
+
+
+def _ref_run(tmp_path_factory, name, fa, fb, extra):
+    """The reference's CPU run of a case, once per session: the same pair + flags serve several parametrisations (fast /
+    diag path, 2 / 4 ranks), and the reference needs about a minute of CPU for the 150k x 140k pairs."""
+    key = (name, tuple(extra))
+    if key not in _REF_CACHE:
+        wd = str(tmp_path_factory.mktemp("ref_" + name) / "w")
+        _run(os.path.join(O.REF_DIR, "oracle_cpu"), fa, fb, wd, extra)
+        _REF_CACHE[key] = wd
+    return _REF_CACHE[key]
+
+
 def _files(d):
     out = {}
     for base, _dirs, names in os.walk(d):
@@ -73,14 +87,14 @@ CASES = [
 
 @pytest.mark.parametrize("name,m,n,hom,extra,sr", CASES, ids=[c[0] for c in CASES])
 @pytest.mark.parametrize("path", ["fast", "diag"])
-def test_full_pipeline_matches_reference(tmp_path, name, m, n, hom, extra, sr, path):
+def test_full_pipeline_matches_reference(tmp_path, tmp_path_factory, name, m, n, hom, extra, sr, path):
     _need_binaries()
     a, b = synth.make_pair(m, n, [hom], 0.05, 0.02, 0.02, 0, 11)
     fa, fb = str(tmp_path / "A.fa"), str(tmp_path / "B.fa")
     synth.write_fasta(fa, a, "A")
     synth.write_fasta(fb, b, "B")
-    w_ref, w_new = str(tmp_path / "ref"), str(tmp_path / "new")
-    _run(os.path.join(O.REF_DIR, "oracle_cpu"), fa, fb, w_ref, extra)
+    w_new = str(tmp_path / "new")
+    w_ref = _ref_run(tmp_path_factory, name, fa, fb, extra)
     _run(CUDALIGN, fa, fb, w_new, extra + (["--no-fast-path"] if path == "diag" else []))
     nrows = _compare(w_ref, w_new, sr)
     if sr:
@@ -97,7 +111,7 @@ MGPU_CASES = [
 
 @pytest.mark.parametrize("name,m,n,hom,extra,sr", MGPU_CASES, ids=[c[0] for c in MGPU_CASES])
 @pytest.mark.parametrize("gpus", ["0,0", "0,0,0,0"])
-def test_multi_gpu_pipeline_matches_reference(tmp_path, name, m, n, hom, extra, sr, gpus):
+def test_multi_gpu_pipeline_matches_reference(tmp_path, tmp_path_factory, name, m, n, hom, extra, sr, gpus):
     """build/cudalign --gpus=...: stage 1 on the block-cyclic chain (here: several ranks sharing device 0; with real
     device lists the same code path runs over NVLink, tests/test_mgpu_gpu.py), stages 2-6 on the first GPU.  The
     artefacts must be the reference's, byte for byte -- special rows included: they are assembled from the chunks of all
@@ -107,8 +121,8 @@ def test_multi_gpu_pipeline_matches_reference(tmp_path, name, m, n, hom, extra, 
     fa, fb = str(tmp_path / "A.fa"), str(tmp_path / "B.fa")
     synth.write_fasta(fa, a, "A")
     synth.write_fasta(fb, b, "B")
-    w_ref, w_new = str(tmp_path / "ref"), str(tmp_path / "new")
-    _run(os.path.join(O.REF_DIR, "oracle_cpu"), fa, fb, w_ref, extra)
+    w_new = str(tmp_path / "new")
+    w_ref = _ref_run(tmp_path_factory, name, fa, fb, extra)
     nranks = gpus.count(",") + 1
     _run(CUDALIGN, fa, fb, w_new, extra + [f"--gpus={gpus}"],
          env={"B200_GROUP_WARPS_PER_SM": str(16 // nranks), "B200_GROUP_MIN_CELLS": "0", "B200_CHAIN_CHUNK": "3000", "B200_WATCHDOG_S": "30"})
