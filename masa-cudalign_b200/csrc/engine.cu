@@ -562,6 +562,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	if (!p || !out) { h->err = "b200_align_partition: bad arguments"; return 1; }
 	if (p->reserved[0] & B200_MGPU_CHAIN) return chain_align(&h, 1, p, cb, out);
 	memset(out, 0, sizeof(*out));
+	struct timespec ts_entry; clock_gettime(CLOCK_MONOTONIC, &ts_entry);
 	const int m = p->i1 - p->i0, n = p->j1 - p->j0;
 	if (m <= 0 || n <= 0 || p->i0 < 0 || p->j0 < 0 || p->i1 > h->n0 || p->j1 > h->n1) { h->err = "b200_align_partition: partition outside the sequences"; return 1; }
 	CU(h, cudaSetDevice(h->cfg.device));
@@ -664,7 +665,10 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	CU(h, cudaMemsetAsync(h->progress.p, 0, njobs * sizeof(int), h->stream));
 
 	static const bool dbg = getenv("B200_DEBUG") != nullptr;
-	if (dbg) fprintf(stderr, "[b200] launch: %d strips, prune=%d track=%d kind=%d\n", njobs, (int)(p->prune && sw), track, kind);
+	auto now_ms = []() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+	const double t_launch = now_ms();
+	if (dbg) fprintf(stderr, "[b200] launch: %d strips, prune=%d track=%d kind=%d, %zu special rows; %.1f ms of setup (buffers, borders, jobs)\n", njobs, (int)(p->prune && sw), track, kind, sr_ids.size(),
+	                 t_launch - (ts_entry.tv_sec * 1e3 + ts_entry.tv_nsec * 1e-6));
 	// ---- the alignment itself: one persistent launch
 	// block pruning: SW stage 1 behind a zero first column, as in the reference (sw_stage1.cpp:219-225); a partition that
 	// starts from a real left border is pruned only by the chain instances, which carry that border in the pruning test
@@ -720,7 +724,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 	CU(h, cudaMemcpyAsync(h->hscalars.p, h->scalars.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));
 	CU(h, cudaGetLastError());
-	if (dbg) fprintf(stderr, "[b200] kernel done, stop=%d\n", h->hscalars.p[2]);
+	if (dbg) fprintf(stderr, "[b200] kernel done, stop=%d; %zu of %zu special rows streamed while it ran; %.1f ms since launch\n", h->hscalars.p[2], rows_streamed, sr_ids.size(), now_ms() - t_launch);
 	if (dbg && h->hscalars.p[2] != 0) {
 		std::vector<int> prog(njobs);
 		cudaMemcpy(prog.data(), h->progress.p, njobs * sizeof(int), cudaMemcpyDeviceToHost);
@@ -792,6 +796,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			}
 		}
 		if (cb->dispatch_score && track && best.i >= 0) cb->dispatch_score(cb->ctx, best);
+		if (dbg) fprintf(stderr, "[b200] artefacts dispatched; %.1f ms since launch\n", now_ms() - t_launch);
 	}
 	return 0;
 }
