@@ -260,6 +260,44 @@ def full_alignment_leg(td):
     return out
 
 
+def reference_gpu_leg(td, timeout_s=120):
+    """Optional kernel-vs-kernel context (SURVEY.md 8d "Reference GPU baseline"): stage 1 of the BASELINE cfg1 pair (1M x 1M, which
+    under-fills a B200: 977 strips on 2368 warp slots) and of cfg3 at scale 0.1 (2.3M x 2.5M)
+    through the reference's OWN CUDA aligner built for sm_100 (oracle/_ref/cudalign_ref_gpu: R/src/CUDAligner.cu kernels and
+    host loop unmodified, texture references replaced by __ldg pointers -- oracle/build_ref_gpu.sh) and through build/cudalign,
+    same FASTA files, same MASA-Core driver, same flags.  Time = MASA-Core's ALIGN timer around alignPartition.  N = 1 only;
+    never part of `value`."""
+    import re
+    import synth
+    ref = os.path.join(ROOT, "oracle", "_ref", "cudalign_ref_gpu")
+    new = os.path.join(ROOT, "build", "cudalign")
+    if not (os.path.exists(ref) and os.path.exists(new)):
+        return {"unavailable": "oracle/_ref/cudalign_ref_gpu or build/cudalign not built (both need the reference mount at build time)"}
+    res = {"reference_build": "R/src/CUDAligner.cu + CUDAligner.cpp unmodified except texture references -> __ldg (oracle/build_ref_gpu.sh), -arch=sm_100",
+           "pairs": []}
+    for cfg, scale in (("cfg1", 1.0), ("cfg3", 0.1)):
+        a, b = synth.make_config(cfg, scale)
+        fa, fb = os.path.join(td, f"{cfg}_A.fa"), os.path.join(td, f"{cfg}_B.fa")
+        synth.write_fasta(fa, a, f"synth_{cfg}_A"); synth.write_fasta(fb, b, f"synth_{cfg}_B")
+        out = {"workload": f"{cfg} x {scale}: {a.size} x {b.size} synthetic pair, SW stage 1 with block pruning (--stage-1 --no-flush), time = MASA-Core's ALIGN timer"}
+        for key, exe in (("reference_gpu", ref), ("b200", new)):
+            wd = os.path.join(td, f"w_{cfg}_{key}")
+            p = subprocess.run([exe, f"--work-dir={wd}", "--clear", "--verbose=0", "--stage-1", "--no-flush", fa, fb], cwd=td,
+                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout_s)
+            if p.returncode != 0:
+                out[key] = {"rc": p.returncode, "tail": p.stdout[-300:]}
+                continue
+            st = open(os.path.join(wd, "statistics_01.00")).read()
+            ms = float(re.search(r"ALIGN:\s+([0-9.]+)", st).group(1))
+            out[key] = {"align_ms": ms, "gcups": a.size * b.size / ms / 1e6,
+                        "stage1_crosspoint": open(os.path.join(wd, "crosspoints", "crosspoint_01.00")).read().split("\n")[1]}
+        if "gcups" in out.get("reference_gpu", {}) and "gcups" in out.get("b200", {}):
+            out["same_result"] = out["reference_gpu"]["stage1_crosspoint"] == out["b200"]["stage1_crosspoint"]
+            out["speedup"] = out["b200"]["gcups"] / out["reference_gpu"]["gcups"]
+        res["pairs"].append(out)
+    return res
+
+
 # ------------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------------
@@ -276,6 +314,7 @@ def main():
     ap.add_argument("--chunk-cols", type=int, default=0, help="N > 1: column chunk width (0 = automatic, < 0 = one contiguous slice per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-full-alignment", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the optional reference-GPU-kernel context leg (N = 1)")
     ap.add_argument("--no-e2e", action="store_true", help="records of the very large pairs: skip the end-to-end leg")
     ap.add_argument("--no-pruning", action="store_true", help="compute every cell (the reference's --no-block-pruning)")
     args = ap.parse_args()
@@ -437,6 +476,12 @@ def main():
         with tempfile.TemporaryDirectory() as td:
             line["full_alignment"] = full_alignment_leg(td)
         line["full_alignment_s"] = line["full_alignment"].get("wall_s")
+    if world == 1 and not args.no_reference_gpu:
+        try:
+            with tempfile.TemporaryDirectory() as td:
+                line["reference_gpu_kernel"] = reference_gpu_leg(td)
+        except Exception as e:                                    # context only: never costs the bench line
+            line["reference_gpu_kernel"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline and ref_binary() is not None:
         side = min(m, n, 60_000)
         with tempfile.TemporaryDirectory() as td:
