@@ -6,7 +6,7 @@ NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -X
 LIB       := $(PKG)/libb200align.so
 CSRC      := $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.cuh) include/b200align.h
 
-.PHONY: all lib oracle cudalign clean
+.PHONY: all lib oracle cudalign refgpu clean
 all: lib oracle
 
 lib: $(LIB)
@@ -15,6 +15,14 @@ $(LIB): $(CSRC)
 
 oracle:
 	$(MAKE) -C oracle all
+
+# the drop-in binary (needs the read-only reference mount: MASA-Core is compiled from there into build/ref/)
+cudalign: lib
+	$(MAKE) -C $(PKG)/host
+
+# optional measurement baseline: the reference's own CUDA aligner, texture references patched out (oracle/_ref/cudalign_ref_gpu)
+refgpu: oracle
+	bash oracle/build_ref_gpu.sh
 
 clean:
 	rm -f $(LIB)

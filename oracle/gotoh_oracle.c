@@ -9,9 +9,13 @@
  *                           => lexicographically smallest (i,j) among maximal cells
  *   - goal matching         C/libmasa/utils/AlignerUtils.cpp:50-107
  *   - pruning bound         C/libmasa/pruning/AbstractBlockPruning.cpp:70-113
+ *   - stage-4 split         C/stage4/sw_stage4.cpp:87-380,785-852 (split_thread, ort_split_2, merge_partitions)
+ *   - stage-5 traceback     C/stage5/sw_stage5.cpp:86-319,404-424
  * Parity pinning: the reference ships no golden vectors; this file is pinned against
  * the reference's own code compiled from /root/reference (oracle/_ref/oracle_cpu, oracle_cpu_block) by
- * tests/test_oracle_cpu.py and the committed fixtures in tests/golden/.
+ * tests/test_oracle_cpu.py and the committed fixtures in tests/golden/ (reference_runs.json: stage-1 best cells, special-row
+ * files, crosspoints of stages 1-4; stage5_runs.json: what the reference's stage 5 stored in alignment.00.bin, read back with
+ * the reference's own reader; cfg1_stage1.json: BASELINE cfg1 at full size).
  */
 #include "gotoh_oracle.h"
 #include <stdlib.h>

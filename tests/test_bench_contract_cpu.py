@@ -37,3 +37,40 @@ def test_product_arm_has_no_cpu_fallback():
     assert r.returncode != 0
     assert r.stdout.strip() == ""
     assert "no CPU fallback" in r.stderr
+
+
+def test_context_legs_parse_and_degrade(tmp_path, monkeypatch):
+    """The N = 1 context legs of the product arm never cost the bench line: the per-stage split is read from MASA-Core's own
+    statistics file, and the reference-GPU-kernel leg reports `unavailable` where the two binaries do not exist.  With the
+    CPU binaries of oracle/_ref standing in for the two executables the leg's whole flow (FASTA, both runs, ALIGN timer,
+    crosspoint comparison) runs without a GPU."""
+    import shutil
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import bench
+    import synth
+    st = tmp_path / "statistics"
+    st.write_text("#  GLOBAL STATISTICS\n      SEQUENCES:       0.0560 (   1)  avg.:   0.0560\n         STAGE1:      29.1700 (   1)  avg.:  29.1700\n"
+                  "         STAGE5:       0.3220 (   1)  avg.:   0.3220\n          TOTAL:      53.8340\n        Total: 53.8340\n")
+    assert bench.stage_split(str(st)) == {"sequences": 0.056, "stage1": 29.17, "stage5": 0.322, "total": 53.834}
+    assert bench.stage_split(str(tmp_path / "missing")) == {}
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path / "nowhere"))
+    assert "unavailable" in bench.reference_gpu_leg(str(tmp_path))
+    cpu_a, cpu_b = os.path.join(ROOT, "oracle", "_ref", "oracle_cpu"), os.path.join(ROOT, "oracle", "_ref", "oracle_cpu_block")
+    if not (os.path.exists(cpu_a) and os.path.exists(cpu_b)):
+        return
+    fake = tmp_path / "root"
+    (fake / "oracle" / "_ref").mkdir(parents=True)
+    (fake / "build").mkdir()
+    shutil.copy(cpu_a, fake / "oracle" / "_ref" / "cudalign_ref_gpu")
+    shutil.copy(cpu_b, fake / "build" / "cudalign")
+    monkeypatch.setattr(bench, "ROOT", str(fake))
+    real = synth.make_config
+    monkeypatch.setattr(synth, "make_config", lambda name, scale=1.0: real(name, 0.002 if name == "cfg1" else 0.0001))
+    work = tmp_path / "work"
+    work.mkdir()
+    out = bench.reference_gpu_leg(str(work))
+    assert len(out["pairs"]) == 2
+    for pair in out["pairs"]:
+        assert pair["same_result"] is True and pair["speedup"] > 0
+        assert pair["reference_gpu"]["stage1_crosspoint"].count(",") == 3
