@@ -322,7 +322,6 @@ def main():
     if args.impl == "reference":
         return reference_arm(args)
 
-    import numpy as np
     import torch
     from __graft_entry__ import load_package
     b200 = load_package()

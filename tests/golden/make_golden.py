@@ -10,7 +10,6 @@ import hashlib
 import json
 import os
 import struct
-import subprocess
 import sys
 import tempfile
 

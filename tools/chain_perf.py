@@ -9,7 +9,7 @@ exist per SM (a multi-GPU run at N GPUs leaves each GPU with about 1/N of the fr
   python tools/chain_perf.py --strips-per-sm 8 --cols 3000000 --chunk 65536
   python tools/chain_perf.py --config cfg3 --scale 0.1 --prune --chunk 0
 """
-import argparse, importlib.util, json, os, sys, time
+import argparse, importlib.util, json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 import synth

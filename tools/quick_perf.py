@@ -3,7 +3,6 @@
 import argparse, importlib.util, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
-import numpy as np
 import synth
 spec = importlib.util.spec_from_file_location("masa_cudalign_b200", os.path.join(ROOT, "masa-cudalign_b200", "__init__.py"))
 b200 = importlib.util.module_from_spec(spec); spec.loader.exec_module(b200)
