@@ -131,3 +131,30 @@ def test_stage5_restatement_matches_reference(name):
     g0, g1 = O.stage5_gaps(pts, ops, off, ln)
     assert g0 == sorted(al["gaps0"]) and g1 == sorted(al["gaps1"])
     assert al["start"] == [int(pts["i"][0]) + 1, int(pts["j"][0]) + 1] and al["end"] == [int(pts["i"][-1]), int(pts["j"][-1])]
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_stage5_walk_scores_the_global_optimum(seed):
+    """Two independent restatements must agree: the score the stage-5 walk collects over a MATCH -> MATCH partition
+    (sw_stage5.cpp tables + traceback) is the Needleman-Wunsch optimum of the two substrings, i.e. the last cell of the
+    stage-1 recurrence (CPUBlockProcessor cell + InitialCellsReader gap borders).  Also: the walk consumes the partition
+    exactly, and its counters add up to its length."""
+    rng = np.random.default_rng(300 + seed)
+    m, n = int(rng.integers(1, 400)), int(rng.integers(1, 400))
+    a = synth.ACGT[rng.integers(0, 4, size=m)]
+    b = a.copy()[:n] if seed % 2 and n <= m else synth.ACGT[rng.integers(0, 4, size=n)]
+    if seed % 2:                                       # related sequences: sprinkle substitutions
+        b = b.copy()
+        hit = rng.random(b.size) < 0.2
+        b[hit] = synth.ACGT[rng.integers(0, 4, size=int(hit.sum()))]
+    n = b.size
+    pts = np.array([(0, 0, 0, 0), (m, n, 0, 0)], dtype=O.XPOINT)
+    ops, off, ln, st = O.stage5(a, b, pts)
+    nw = O.full_matrix(a, b, O.NW, first_row_type=O.INIT_GAPS, first_col_type=O.INIT_GAPS)
+    assert st["score"] == int(nw["last_col"][-1]["h"])
+    walk = ops[:int(ln[1])]
+    assert int((walk == 0).sum() + (walk == 1).sum()) == m and int((walk == 0).sum() + (walk == 2).sum()) == n
+    assert st["matches"] + st["mismatches"] == int((walk == 0).sum()) and st["gap_ext"] == int((walk != 0).sum())
+    # the reference charges the opening of a gap that runs into the partition's border to the score without counting it in
+    # gapOpen (sw_stage5.cpp:291-311), so the counters explain the score up to that one opening
+    assert st["score"] - (st["matches"] - 3 * st["mismatches"] - 3 * st["gap_open"] - 2 * st["gap_ext"]) in (0, -3)
