@@ -109,3 +109,16 @@ def test_device_function_on_random_partition_chains(host_lib, seed):
     pts = np.array(pts, dtype=O.XPOINT)
     check_against_oracle(host_lib, a, b, pts, False)
     check_against_oracle(host_lib, a, b, pts, True)
+
+
+def test_device_function_at_the_table_limit(host_lib):
+    """Partitions at the reference's table limit (1024 on a side, H_MAX / W_MAX of sw_stage5.cpp:31-32), thin ones, and one cell."""
+    rng = np.random.default_rng(9)
+    m, n = 5000, 5200
+    a, b = synth.make_pair(m, n, [(0, m)], 0.06, 0.03, 0.03, 0, 91)
+    pts = [(0, 0, 0, 0)]
+    for di, dj in [(1024, 1024), (1, 1), (1, 1024), (1024, 1), (33, 32), (32, 33), (700, 900), (1024, 1000)]:
+        pts.append((pts[-1][0] + di, pts[-1][1] + dj, int(rng.integers(0, 3)), 0))
+    pts = np.array(pts, dtype=O.XPOINT)
+    check_against_oracle(host_lib, a, b, pts, False)
+    check_against_oracle(host_lib, a, b, pts, True)
