@@ -4,7 +4,7 @@ NVCC      ?= nvcc
 PKG       := masa-cudalign_b200
 NVFLAGS   := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
 LIB       := $(PKG)/libb200align.so
-CSRC      := $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.cuh) include/b200align.h
+CSRC      := $(wildcard $(PKG)/csrc/*.cu) $(wildcard $(PKG)/csrc/*.cuh) $(wildcard $(PKG)/csrc/*.inl) include/b200align.h
 
 .PHONY: all lib oracle cudalign refgpu clean
 all: lib oracle
