@@ -3,7 +3,7 @@
 // One translation unit: this file holds the handle, the launch helpers and the lifetime calls; the entry points live in
 // engine_sequences.inl, engine_partition.inl, engine_diag.inl, engine_chain.inl, engine_stage4.inl, engine_stage5.inl,
 // included at the end (the kernels are instantiated once, by launch_strips below).
-#include <cuda_runtime.h>
+#include "ptx.cuh"       // <cuda_runtime.h> + the inline-PTX wrappers + B200_LAUNCH
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -308,8 +308,12 @@ int launch_strips(b200_handle* h, int njobs, int recurrence, int track, int kern
 #undef S16_PICK
 	int grid = grid_for(h, fn, njobs, chained);
 	h->last_grid_warps = grid * kWarpsPerBlock;
+#ifdef B200_EMU      // SIMT emulation build of the test suite (tests/emu): the same kernel, run as a function per emulated thread
+	CU(h, emu::launch_kernel(h->stream, dim3(grid), dim3(kWarpsPerBlock * 32), reinterpret_cast<void (*)(const StripParams)>(const_cast<void*>(fn)), sp));
+#else
 	void* args[] = {(void*)&sp};
 	CU(h, cudaLaunchKernel(fn, dim3(grid), dim3(kWarpsPerBlock * 32), args, 0, h->stream));
+#endif
 	h->stat_launches++;
 	return 0;
 }

@@ -53,7 +53,7 @@ int alloc_exchange(b200_handle* h, long long max_rows, long long max_jobs) {
 
 int arm_exchange(b200_handle* h, long long nstrips, long long njobs, int best_word) {
 	const ExLayout l = ex_layout(h->mg.cap_rows, h->mg.cap_strips, h->mg.cap_jobs);
-	chain_arm_kernel<<<512, 256, 0, h->stream>>>(h->mg.block, l.off_events, l.off_queue, nstrips, njobs, h->mg.rank, best_word);
+	B200_LAUNCH(chain_arm_kernel, 512, 256, h->stream, h->mg.block, l.off_events, l.off_queue, nstrips, njobs, h->mg.rank, best_word);
 	h->stat_launches++;
 	CU(h, cudaGetLastError());
 	return 0;
@@ -248,7 +248,7 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 		CU(h, cudaMemsetAsync(h->progress.p, 0, S * sizeof(int), h->stream));
 		{
 			// results start as "none": strips whose jobs all live on other GPUs keep this value
-			fill_const_kernel<<<(2 * S + 255) / 256, 256, 0, h->stream>>>(reinterpret_cast<Cell*>(h->results.p), 2LL * S, -kInf, -1);
+			B200_LAUNCH(fill_const_kernel, (2 * S + 255) / 256, 256, h->stream, reinterpret_cast<Cell*>(h->results.p), 2LL * S, -kInf, -1);
 			h->stat_launches++;
 		}
 		if (custom_row) {
@@ -256,7 +256,7 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 				CU(h, cudaMemcpyAsync(h->busH.p + cc.j0, h0->mg.hrow.p + (cc.j0 - p->j0), (size_t)cc.cols * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 		} else {
 			const int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
-			fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1, 0);
+			B200_LAUNCH(fill_cells_kernel, (n + 255) / 256, 256, h->stream, h->busH.p + p->j0, n, type, 1, 0);
 			h->stat_launches++;
 		}
 		if (h == hr0 && p->first_col_init != B200_INIT_ZEROES) {
@@ -268,7 +268,7 @@ static int chain_align(b200_handle* const* hs, int nlocal, const b200_partition*
 				CU(h, cudaMemcpyAsync(h->left.p, h->hcells.p, ((size_t)m + 1) * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 			} else {
 				const int type = p->first_col_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_col_init;
-				fill_cells_kernel<<<(m + 1 + 255) / 256, 256, 0, h->stream>>>(h->left.p, (long long)m + 1, type, 0, 0);
+				B200_LAUNCH(fill_cells_kernel, (m + 1 + 255) / 256, 256, h->stream, h->left.p, (long long)m + 1, type, 0, 0);
 				h->stat_launches++;
 			}
 		}

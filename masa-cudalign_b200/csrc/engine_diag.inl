@@ -164,7 +164,7 @@ extern "C" int b200_diag_clear_pruned(b200_handle* h, int j0, int j1) {
 	if (j0 < 0 || j1 > h->n1) { h->err = "b200_diag_clear_pruned: bad range"; return 1; }
 	if (j1 <= j0) return 0;
 	long long n = (long long)j1 - j0;
-	fill_const_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(h->busH.p + j0, n, -kInf, -kInf);
+	B200_LAUNCH(fill_const_kernel, (unsigned)((n + 255) / 256), 256, h->stream, h->busH.p + j0, n, -kInf, -kInf);
 	h->stat_launches++;
 	CU(h, cudaGetLastError());
 	return 0;
@@ -190,7 +190,7 @@ extern "C" int b200_match_last_column(b200_handle* h, const b200_cell* buffer, c
 	CU(h, cudaMemcpyAsync(dbase, base, (size_t)len * sizeof(Cell), cudaMemcpyHostToDevice, h->stream));
 	h->hmatchflag.p[0] = INT_MAX;
 	CU(h, cudaMemcpyAsync(h->matchflag.p, h->hmatchflag.p, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-	match_column_kernel<<<(len + 255) / 256, 256, 0, h->stream>>>(dbuf, dbase, len, goal, kGapOpen, h->matchflag.p);
+	B200_LAUNCH(match_column_kernel, (len + 255) / 256, 256, h->stream, dbuf, dbase, len, goal, kGapOpen, h->matchflag.p);
 	h->stat_launches++;
 	CU(h, cudaMemcpyAsync(h->hmatchflag.p, h->matchflag.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
 	CU(h, cudaStreamSynchronize(h->stream));

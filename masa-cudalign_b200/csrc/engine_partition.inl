@@ -142,7 +142,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 		// top border = last row of the previous chunk, already in busH
 	} else if (p->first_row_init == B200_INIT_ZEROES || !(have_cb && cb->receive_first_row)) {
 		int type = p->first_row_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_row_init;
-		fill_cells_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->busH.p + p->j0, n, type, 1, 0);
+		B200_LAUNCH(fill_cells_kernel, (n + 255) / 256, 256, h->stream, h->busH.p + p->j0, n, type, 1, 0);
 		h->stat_launches++;
 		first_row_tail.h = type == B200_INIT_ZEROES ? 0 : -kGapExt * n - (type == B200_INIT_GAPS ? kGapOpen : 0);
 	} else {
@@ -163,7 +163,7 @@ extern "C" int b200_align_partition(b200_handle* h, const b200_partition* p, con
 			CU(h, cudaStreamSynchronize(h->stream));
 		} else {
 			int type = p->first_col_init == B200_INIT_CUSTOM ? B200_INIT_ZEROES : p->first_col_init;
-			fill_cells_kernel<<<(m + 1 + 255) / 256, 256, 0, h->stream>>>(h->left.p, (long long)m + 1, type, row_offset, 0);
+			B200_LAUNCH(fill_cells_kernel, (m + 1 + 255) / 256, 256, h->stream, h->left.p, (long long)m + 1, type, row_offset, 0);
 			h->stat_launches++;
 		}
 	}

@@ -45,8 +45,8 @@ extern "C" int b200_set_sequences(b200_handle* h, const char* seq0, int seq0_len
 		CU(h, h->s1p.reserve(w1 + 1));
 		CU(h, cudaMemcpyAsync(h->s0p.p, h->hpack.p, w0 * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
 		CU(h, cudaMemcpyAsync(h->s1p.p, h->hpack.p + w0, w1 * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
-		if (seq0_len) unpack2_kernel<<<(seq0_len + 255) / 256, 256, 0, h->stream>>>(h->s0p.p, h->s0.p, seq0_len);
-		if (seq1_len) unpack2_kernel<<<(seq1_len + 255) / 256, 256, 0, h->stream>>>(h->s1p.p, h->s1.p, seq1_len);
+		if (seq0_len) B200_LAUNCH(unpack2_kernel, (seq0_len + 255) / 256, 256, h->stream, h->s0p.p, h->s0.p, seq0_len);
+		if (seq1_len) B200_LAUNCH(unpack2_kernel, (seq1_len + 255) / 256, 256, h->stream, h->s1p.p, h->s1.p, seq1_len);
 		h->stat_launches += 2;
 	} else {
 		CU(h, cudaMemcpyAsync(h->s0.p, seq0, (size_t)seq0_len, cudaMemcpyHostToDevice, h->stream));

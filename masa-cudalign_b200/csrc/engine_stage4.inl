@@ -85,8 +85,8 @@ extern "C" int b200_stage4_round(b200_handle* h, const b200_xpoint* in, int n, i
 	if (!h->s4.rev_valid) {
 		CU(h, h->s4.s0r.reserve((size_t)L0 + 64));
 		CU(h, h->s4.s1r.reserve((size_t)L1 + 64));
-		s4_reverse_kernel<<<(L0 + 255) / 256, 256, 0, h->stream>>>(h->s0.p, h->s4.s0r.p, L0);
-		s4_reverse_kernel<<<(L1 + 255) / 256, 256, 0, h->stream>>>(h->s1.p, h->s4.s1r.p, L1);
+		B200_LAUNCH(s4_reverse_kernel, (L0 + 255) / 256, 256, h->stream, h->s0.p, h->s4.s0r.p, L0);
+		B200_LAUNCH(s4_reverse_kernel, (L1 + 255) / 256, 256, h->stream, h->s1.p, h->s4.s1r.p, L1);
 		h->stat_launches += 2;
 		h->s4.rev_valid = true;
 	}
@@ -109,7 +109,7 @@ extern "C" int b200_stage4_round(b200_handle* h, const b200_xpoint* in, int n, i
 		if (ng == 0) continue;
 		CU(h, cudaMemcpyAsync(h->s4.halves.p + hoff, pl.halves[g].data(), ng * sizeof(S4Half), cudaMemcpyHostToDevice, h->stream));
 		CU(h, cudaMemcpyAsync(h->jobs.p + joff, pl.jobs[g].data(), njg * sizeof(StripJob), cudaMemcpyHostToDevice, h->stream));
-		s4_fill_kernel<<<ng, 128, 0, h->stream>>>(h->s4.halves.p + hoff, ng, h->s4.bus[g].p, h->s4.left.p);
+		B200_LAUNCH(s4_fill_kernel, ng, 128, h->stream, h->s4.halves.p + hoff, ng, h->s4.bus[g].p, h->s4.left.p);
 		h->stat_launches++;
 		h->ov.s0 = rows_seq[g]; h->ov.s1 = cols_seq[g]; h->ov.busH = h->s4.bus[g].p;
 		h->ov.left = h->s4.left.p; h->ov.job_off = (int)joff; h->ov.counter = h->scalars.p + 8 + g;
@@ -119,7 +119,7 @@ extern "C" int b200_stage4_round(b200_handle* h, const b200_xpoint* in, int n, i
 		hoff += ng; joff += njg;
 	}
 	CU(h, cudaMemsetAsync(h->scalars.p + 3, 0, sizeof(int), h->stream));
-	s4_match_kernel<<<(nparts * 32 + 127) / 128, 128, 0, h->stream>>>(h->s4.parts.p, nparts, h->s4.bus[0].p, h->s4.bus[1].p, h->s4.bus[2].p,
+	B200_LAUNCH(s4_match_kernel, (nparts * 32 + 127) / 128, 128, h->stream, h->s4.parts.p, nparts, h->s4.bus[0].p, h->s4.bus[1].p, h->s4.bus[2].p,
 	                                                                   h->s4.bus[3].p, h->s4.left.p, h->s4.left.p, h->s4.out.p, h->scalars.p + 3);
 	h->stat_launches++;
 	std::vector<XPoint> tmp(n);

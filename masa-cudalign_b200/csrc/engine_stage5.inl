@@ -49,7 +49,7 @@ extern "C" int b200_stage5(b200_handle* h, const b200_xpoint* pts, int n, unsign
 	std::vector<S5Out> outs(ns + nb);
 	if (ns) {
 		CU(h, cudaMemcpyAsync(h->s5.parts.p, small.data(), ns * sizeof(S5Part), cudaMemcpyHostToDevice, h->stream));
-		s5_local_kernel<<<(unsigned)((ns + 63) / 64), 64, 0, h->stream>>>(h->s0.p, h->s1.p, h->s5.parts.p, (int)ns, h->s5.ops.p, h->s5.out.p);
+		B200_LAUNCH(s5_local_kernel, (unsigned)((ns + 63) / 64), 64, h->stream, h->s0.p, h->s1.p, h->s5.parts.p, (int)ns, h->s5.ops.p, h->s5.out.p);
 		h->stat_launches++;
 	}
 	// the global variant in batches that fit the flag budget (a batch always takes at least one partition)
@@ -66,7 +66,7 @@ extern "C" int b200_stage5(b200_handle* h, const b200_xpoint* pts, int n, unsign
 		}
 		CU(h, h->s5.rows.reserve((size_t)rows)); CU(h, h->s5.flags.reserve((size_t)flags));
 		CU(h, cudaMemcpyAsync(h->s5.parts.p + ns + done, big.data() + done, (end - done) * sizeof(S5Part), cudaMemcpyHostToDevice, h->stream));
-		s5_global_kernel<<<(unsigned)((end - done + 63) / 64), 64, 0, h->stream>>>(h->s0.p, h->s1.p, h->s5.parts.p + ns + done, (int)(end - done), h->s5.ops.p,
+		B200_LAUNCH(s5_global_kernel, (unsigned)((end - done + 63) / 64), 64, h->stream, h->s0.p, h->s1.p, h->s5.parts.p + ns + done, (int)(end - done), h->s5.ops.p,
 		                                                                           h->s5.rows.p, h->s5.flags.p, h->s5.out.p + ns + done);
 		h->stat_launches++;
 		done = end;

@@ -15,8 +15,8 @@
 // The same kernels run the "diag" compatibility path: there a job is one block of the reference's grid and
 // jobs of one launch do not depend on each other.
 #pragma once
-#include <cuda_runtime.h>
 #include <stdint.h>
+#include "ptx.cuh"
 
 namespace b200 {
 
@@ -147,41 +147,10 @@ enum StripOpt : int {
 	OPT_DEFER_RELEASE = 64,  // steady state: publish a block's counter one block later, when its stores have long landed
 };
 
-__device__ __forceinline__ int ld_acquire(const int* p) {
-	int v;
-	asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v) {
-	asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_relaxed(const int* p) {
-	int v;
-	asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-	int v;
-	asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ int ld_relaxed_sys(const int* p) {
-	int v;
-	asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-	asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 // lexicographic "better" for best cells: higher score, then smaller i, then smaller j
 // (CPUBlockProcessor.cpp:154-158 row-major strict '<' + BestScoreList.hpp:30-38)
 __device__ __forceinline__ bool better(int s, int i, int j, int bs, int bi, int bj) {
 	return s > bs || (s == bs && (i < bi || (i == bi && j < bj)));
-}
-__device__ __forceinline__ unsigned long long global_ns() {
-	unsigned long long t;
-	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-	return t;
 }
 // Spin-wait watchdog.  Waits in the strip chain are legitimately as long as a whole sweep of a column chunk on another
 // GPU, so the limit is a TIME without any observable progress (StripParams::watchdog_ns, sized by the engine from the
@@ -233,11 +202,6 @@ __device__ __forceinline__ void chain_push(int* queue, int* tail, int job) {
 	__threadfence_system();
 	const int slot = atomicAdd_system(tail, 1);
 	st_release_sys(queue + slot, job);
-}
-__device__ __forceinline__ unsigned sm_id() {
-	unsigned v;
-	asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
-	return v;
 }
 // index of this warp's scheduler in StripParams::sm_load (a CTA's four warps sit on the four sub-partitions of its SM)
 __device__ __forceinline__ unsigned sched_slot() { return 4u * sm_id() + ((threadIdx.x >> 5) & 3u); }

@@ -59,13 +59,6 @@ __device__ __forceinline__ int lo16(unsigned v) { return (int)(short)(v & 0xffff
 __device__ __forceinline__ int hi16(unsigned v) { return (int)(short)(v >> 16); }
 __device__ __forceinline__ int clamp16(int v) { return v < kNeg ? kNeg : (v > 32767 ? 32767 : v); }
 __device__ __forceinline__ unsigned dup2(int v) { return pack2(v, v); }
-// raw PRMT: unlike __byte_perm (which masks the selector with 0x7777) bit 3 of a selector nibble replicates the
-// sign bit of the selected byte, which is how one instruction yields two sign-extended s16 scores
-__device__ __forceinline__ unsigned prmt(unsigned a, unsigned b, unsigned sel) {
-	unsigned d;
-	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
-	return d;
-}
 __device__ __forceinline__ unsigned thr_pack(int thr, int base) {
 	if (thr == INT_MIN) return 0x80008000u;
 	const long long d = (long long)thr - base;
@@ -150,7 +143,7 @@ struct StripS16 {
 #pragma unroll
 			for (int r = 0; r < R; r++) {
 				unsigned sc;
-				if (LUT) asm("ld.shared.u32 %0, [%1];" : "=r"(sc) : "r"(lrow + s.sel[r]));
+				if (LUT) sc = lds32_pure(lrow + s.sel[r]);
 				else sc = prmt(s.pa, s.pb, s.sel[r]);
 				const unsigned e = __viaddmax_s16x2(s.E[r], M2, s.T[r]);
 				const unsigned x = SW ? __viaddmax_s16x2(dT, sc, s.Zp) : __vadd2(dT, sc);
@@ -233,11 +226,6 @@ struct StripS16 {
 	// Takes and returns scalars only, so the register-resident State never has its address taken.
 	// `cand` is the 32-bit shared-memory address of the ring: a generic pointer argument would have its 64-bit address
 	// materialised in the hot loop of the caller
-	__device__ __forceinline__ static unsigned lds32(unsigned addr) {
-		unsigned v;
-		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-		return v;
-	}
 	__device__ __noinline__ static Best drain_scan(unsigned cand, int ncand, int rows, int c0, int c1, int i0, int j0,
 	                                               int base, int lane, Best b) {
 		__syncwarp();
@@ -309,7 +297,7 @@ struct StripS16 {
 
 		State s;
 		s.lut = lut_addr + 4u * (unsigned)lane;
-		asm volatile("mov.u32 %0, %0;" : "+r"(s.lut));          // opaque: keep it in a register instead of re-deriving it every step
+		keep_in_register(s.lut);                               // instead of re-deriving it every step
 		// ---- left border; the frame starts at the H of the corner
 		const Cell* lb = left_border(p, cx);
 		int base = 0;
