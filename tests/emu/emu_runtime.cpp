@@ -6,7 +6,7 @@
 //     between "devices" make real progress; larger grids are drained block by block by those threads
 //   * streams: one worker thread each, tasks in order (copies, memsets, event records, kernel launches)
 //   * devices: B200_EMU_DEVICES (default 4) identical "sm_100" devices of B200_EMU_SMS (default 2) SMs sharing the host's
-//     memory; peer access always possible; CUDA IPC (one process per GPU) is not emulated
+//     memory; peer access always possible; CUDA IPC works inside one process only (one process per GPU is not emulated)
 //   * B200_EMU_SHUFFLE=<seed>: fibers of a CTA are visited in a random order that changes every pass (protocol fuzzing)
 #include <cuda_runtime.h>
 
@@ -17,6 +17,7 @@
 #include <thread>
 
 #include <sched.h>
+#include <unistd.h>
 #include <sys/mman.h>
 
 #if !defined(__x86_64__)
@@ -58,7 +59,7 @@ int env_int(const char* name, int dflt) {
 }
 
 constexpr size_t kStackBytes = 128 * 1024;
-enum : int { RUNNABLE = 0, BLOCKED = 1, DONE = 2 };
+enum : int { RUNNABLE = 0, BLOCKED = 1, DONE = 2, BLOCKED_CTA = 3 };   // BLOCKED: at a warp rendezvous, BLOCKED_CTA: at __syncthreads
 
 struct Warp;
 struct Fiber {
@@ -106,7 +107,7 @@ void release_block(Block* b) {
 	b->bar_arrived = 0;
 	b->bar_gen++;
 	for (auto& f : b->fibers)
-		if (f.state == BLOCKED) f.state = RUNNABLE;
+		if (f.state == BLOCKED_CTA) f.state = RUNNABLE;
 }
 
 void fiber_main() {
@@ -225,7 +226,7 @@ void block_barrier() {
 	f->polls = 0;
 	b->progress = true;
 	if (++b->bar_arrived >= b->alive) { release_block(b); return; }
-	f->state = BLOCKED;
+	f->state = BLOCKED_CTA;
 	to_scheduler();
 }
 void sleep_yield() { to_scheduler(); }
@@ -365,9 +366,23 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
 	*ms = (float)(b->t_ms.load() - a->t_ms.load());
 	return cudaSuccess;
 }
-cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void*) { memset(h, 0, sizeof(*h)); return cudaErrorNotSupported; }
-cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaErrorNotSupported; }
+// CUDA IPC inside ONE process only (a handle is the pointer plus the pid): enough for the self-chain tests, where a GPU is
+// its own neighbour; one process per GPU (torchrun) is not emulated
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+	memset(h, 0, sizeof(*h));
+	const long long pid = (long long)getpid();
+	memcpy(h->reserved, &p, sizeof(p));
+	memcpy(h->reserved + 8, &pid, sizeof(pid));
+	return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
+	long long pid = 0;
+	memcpy(&pid, h.reserved + 8, sizeof(pid));
+	if (pid != (long long)getpid()) return cudaErrorNotSupported;
+	memcpy(p, h.reserved, sizeof(*p));
+	return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
 
 // test hooks (not part of the C ABI of the product library)
 extern "C" long long b200_emu_s16_overflows(void) { return emu::g_s16_overflow.load(); }

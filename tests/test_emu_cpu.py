@@ -1,0 +1,103 @@
+"""The GPU parity tests, run where no GPU exists: on the SIMT emulation build of the library (tests/emu/).
+
+tests/emu/ compiles the library's own sources -- masa-cudalign_b200/csrc/engine.cu with every kernel, the strip-chain protocol,
+the multi-GPU chain, stage 4 and stage 5 -- for the host CPU: one fiber per CUDA thread, one OS thread per co-resident CTA, a
+worker thread per stream, several emulated devices (tests/emu/cuda_runtime.h).  The result has the C ABI of libb200align.so,
+so the `-m gpu` test files run on it UNCHANGED (in a subprocess, with the package's B200_LIB development switch pointing at
+the emulation and, for build/cudalign, LD_PRELOAD): same inputs, same oracle, same bit-exact assertions.
+
+This checks the C++ semantics of the device code and the protocols between warps, CTAs, streams and devices.  It is not a
+CPU path of the product (nothing outside tests/ can load it, libb200align.so itself still refuses to run without a GPU:
+tests/test_cabi_cpu.py) and not a substitute for the run on the B200: memory-ordering strength, convergence and timing are
+properties of the hardware.  Cases are the small parametrisations of each GPU test file, sized for a few minutes in total."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+import build_emu  # noqa: E402
+
+pytestmark = pytest.mark.skipif(not build_emu.available(), reason="the SIMT emulation needs g++ on x86-64")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    return build_emu.build()
+
+
+def _run_gpu_tests(emu_lib, files, k, extra_env=None, preload=False, timeout=900):
+    env = dict(os.environ)
+    env["B200_LIB"] = emu_lib
+    if preload:
+        env["LD_PRELOAD"] = emu_lib          # build/cudalign links libb200align.so: the emulation's b200_* symbols take precedence
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-p", "no:cacheprovider", "--timeout", "600", *files]
+    if k:
+        cmd += ["-k", k]
+    r = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=timeout)
+    tail = r.stdout[-3000:]
+    m = re.search(r"(\d+) passed", r.stdout)
+    passed = int(m.group(1)) if m else 0
+    assert r.returncode == 0 and "failed" not in r.stdout.splitlines()[-1], tail
+    assert not re.search(r"\d+ skipped", r.stdout.splitlines()[-1]), "a selected test skipped itself:\n" + tail
+    return passed
+
+
+def test_emulation_is_what_runs(emu_lib):
+    """The subprocesses below really load the emulation: it exports the emulation-only probe, the product library does not."""
+    import ctypes
+    lib = ctypes.CDLL(emu_lib)
+    assert lib.b200_emu_is_emulation() == 1
+    prod = os.path.join(ROOT, "masa-cudalign_b200", "libb200align.so")
+    if os.path.exists(prod):
+        assert not hasattr(ctypes.CDLL(prod), "b200_emu_is_emulation")
+
+
+def test_stage1_whole_partition_path(emu_lib):
+    """Both strip kernels against the oracle: best cell, last row / column, special rows, NW, custom borders, N / IUPAC
+    bytes, packed sequences, -INF borders, on-device pruning, one non-default variant of the strip-chain protocol."""
+    k = ("test_sw_best_and_borders or test_special_rows or test_nw_global or test_custom_borders_subpartition "
+         "or test_pruning_keeps_best_exact[20000-20000 "
+         "or test_mixed_alphabet or test_chain_protocol_variants_are_exact[0] or test_chain_protocol_variants_are_exact[127] "
+         "or test_packed_and_byte_sequences_agree or test_nw_border_with_minus_inf")
+    assert _run_gpu_tests(emu_lib, ["tests/test_stage1_gpu.py"], k) >= 30
+
+
+def test_diag_primitives_matcher_stage4_stage5(emu_lib):
+    """Every diag primitive (the reference's per-diagonal contract), the device goal matcher, the batched stage-4 split
+    against the reference's crosspoint_04 and the stage-5 traceback against the reference's alignments."""
+    n = _run_gpu_tests(emu_lib, ["tests/test_diag_gpu.py", "tests/test_match_gpu.py", "tests/test_stage4_gpu.py", "tests/test_stage5_gpu.py"], None)
+    assert n >= 60
+
+
+def test_chain_on_one_and_several_emulated_devices(emu_lib):
+    """The block-cyclic chain: a device that is its own neighbour, 2-4 ranks of a group, pruning across chunk borders, NW,
+    re-arming with other sequences; the watchdog reports a stuck dependency and tolerates a slow neighbour."""
+    k = ("test_self_chain_sw_matches_oracle[2049-1500-257 or test_self_chain_sw_matches_oracle[700-900 or test_self_chain_sw_matches_oracle[1-1 "
+         "or test_self_chain_sw_matches_oracle[3000-3000 or test_self_chain_rearm or test_self_chain_nw_global "
+         "or test_self_chain_custom_borders or test_group_on_one_device_sw[s16x2-4-700] or test_stuck_dependency")
+    assert _run_gpu_tests(emu_lib, ["tests/test_chain_gpu.py", "tests/test_watchdog_gpu.py"], k) >= 16
+
+
+def test_scheduling_order_does_not_matter(emu_lib):
+    """The same chain and stage-1 cases with the fibers of every CTA visited in a random order that changes each pass: the
+    results may not depend on which warp or lane runs first (a cheap search for protocol races)."""
+    k = ("test_sw_best_and_borders[2049-1500 or test_special_rows[9000-3000-s16x2] or test_self_chain_sw_matches_oracle[2049-1500-257 "
+         "or test_group_on_one_device_sw[s16x2-4-700] or test_self_chain_rearm")
+    assert _run_gpu_tests(emu_lib, ["tests/test_stage1_gpu.py", "tests/test_chain_gpu.py"], k, {"B200_EMU_SHUFFLE": "11"}) >= 6
+
+
+def test_drop_in_binary_full_pipeline(emu_lib):
+    """build/cudalign (B200Aligner + the reference's unmodified MASA-Core, stages 1-6, stage 4 and 5 substitutes) against the
+    reference's CPU run: crosspoint files, alignment.00.bin / .txt, special rows -- fast path, diag path, and stage 1 on a
+    chain of two ranks."""
+    if not (os.path.exists(os.path.join(ROOT, "build", "cudalign")) and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "oracle_cpu"))):
+        pytest.skip("build/cudalign or oracle/_ref/oracle_cpu not built (they need the reference mount at build time)")
+    f = "tests/test_pipeline_gpu.py::"
+    ids = [f + "test_full_pipeline_matches_reference[fast-sw_3k]", f + "test_full_pipeline_matches_reference[diag-sw_3k]",
+           f + "test_full_pipeline_matches_reference[fast-sw_40k_pruning_ram]", f + "test_multi_gpu_pipeline_matches_reference[0,0-nw_global_20k]"]
+    assert _run_gpu_tests(emu_lib, ids, None, preload=True, timeout=1500) == 4
