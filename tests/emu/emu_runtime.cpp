@@ -6,7 +6,10 @@
 //     between "devices" make real progress; larger grids are drained block by block by those threads
 //   * streams: one worker thread each, tasks in order (copies, memsets, event records, kernel launches)
 //   * devices: B200_EMU_DEVICES (default 4) identical "sm_100" devices of B200_EMU_SMS (default 2) SMs sharing the host's
-//     memory; peer access always possible; CUDA IPC works inside one process only (one process per GPU is not emulated)
+//     memory; peer access always possible; CUDA IPC inside one process, and between processes with B200_EMU_SHM=1
+//   * B200_EMU_GUARD=1: guard pages around every device / pinned allocation (out-of-bounds accesses fault)
+//   * B200_EMU_POISON=<byte>: fill pattern of fresh allocations (default 0xA5 = a large negative int; 0x3F = a large positive one):
+//     results may not depend on it
 //   * B200_EMU_SHUFFLE=<seed>: fibers of a CTA are visited in a random order that changes every pass (protocol fuzzing)
 #include <cuda_runtime.h>
 
@@ -16,6 +19,7 @@
 #include <random>
 #include <thread>
 
+#include <fcntl.h>
 #include <sched.h>
 #include <unistd.h>
 #include <sys/mman.h>
@@ -324,17 +328,75 @@ cudaError_t cudaDeviceCanAccessPeer(int* can, int, int) { *can = 1; return cudaS
 cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
 cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 
+// B200_EMU_GUARD=1: every allocation ends right in front of an inaccessible page (and starts behind one), so a kernel or a
+// copy that reads or writes past a buffer dies with SIGSEGV at the faulting instruction instead of touching a neighbour
+namespace {
+std::mutex g_guard_m;
+std::vector<std::tuple<void*, void*, size_t>> g_guarded;     // user pointer, mapping base, mapping length
+}
+// B200_EMU_SHM=1 (one process per emulated GPU, tests/mgpu_check.py under torchrun with gloo): device allocations live in
+// memfd-backed shared mappings, so that cudaIpcOpenMemHandle in ANOTHER process can map them (through /proc/<pid>/fd/<fd>)
+// and the chain's peer stores and system-scope atomics cross process borders as they cross NVLink
+namespace {
+struct ShmAlloc { void* p; size_t len; int fd; bool imported; };
+std::vector<ShmAlloc> g_shm;
+}
 cudaError_t cudaMalloc(void** p, size_t bytes) {
+	if (env_int("B200_EMU_SHM", 0)) {
+		const size_t len = (std::max<size_t>(bytes, 1) + 4095) & ~(size_t)4095;
+		const int fd = memfd_create("b200emu", 0);
+		if (fd < 0 || ftruncate(fd, (off_t)len) != 0) return cudaErrorMemoryAllocation;
+		void* q = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+		if (q == MAP_FAILED) { close(fd); return cudaErrorMemoryAllocation; }
+		memset(q, env_int("B200_EMU_POISON", 0xA5), std::min<size_t>(len, (size_t)64 << 20));
+		std::lock_guard<std::mutex> lk(g_guard_m);
+		g_shm.push_back({q, len, fd, false});
+		*p = q;
+		return cudaSuccess;
+	}
+	if (env_int("B200_EMU_GUARD", 0)) {
+		const size_t page = 4096, body = (std::max<size_t>(bytes, 1) + page - 1) & ~(page - 1), len = body + 2 * page;
+		char* base = static_cast<char*>(mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0));
+		if (base == MAP_FAILED) return cudaErrorMemoryAllocation;
+		mprotect(base, page, PROT_NONE);
+		mprotect(base + page + body, page, PROT_NONE);
+		char* user = base + page + body - ((bytes + 15) & ~(size_t)15);        // 16-byte aligned, ends at the guard page
+		memset(base + page, env_int("B200_EMU_POISON", 0xA5), body);
+		std::lock_guard<std::mutex> lk(g_guard_m);
+		g_guarded.emplace_back(user, base, len);
+		*p = user;
+		return cudaSuccess;
+	}
 	const size_t sz = (std::max<size_t>(bytes, 1) + 255) & ~(size_t)255;
 	*p = aligned_alloc(256, sz);
 	if (!*p) return cudaErrorMemoryAllocation;
-	memset(*p, 0xA5, std::min<size_t>(sz, 1 << 20));     // device memory is not zero-initialised: make reliance on it visible
+	memset(*p, env_int("B200_EMU_POISON", 0xA5), std::min<size_t>(sz, (size_t)64 << 20));     // device memory is not zero-initialised: make reliance on it visible
 	return cudaSuccess;
 }
-cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFree(void* p) {
+	if (!p) return cudaSuccess;
+	{
+		std::lock_guard<std::mutex> lk(g_guard_m);
+		for (size_t k = 0; k < g_shm.size(); k++)
+			if (g_shm[k].p == p) {
+				munmap(g_shm[k].p, g_shm[k].len);
+				if (g_shm[k].fd >= 0) close(g_shm[k].fd);
+				g_shm.erase(g_shm.begin() + k);
+				return cudaSuccess;
+			}
+		for (size_t k = 0; k < g_guarded.size(); k++)
+			if (std::get<0>(g_guarded[k]) == p) {
+				munmap(std::get<1>(g_guarded[k]), std::get<2>(g_guarded[k]));
+				g_guarded.erase(g_guarded.begin() + k);
+				return cudaSuccess;
+			}
+	}
+	free(p);
+	return cudaSuccess;
+}
 cudaError_t cudaMallocHost(void** p, size_t bytes) { return cudaMalloc(p, bytes); }
 cudaError_t cudaHostAlloc(void** p, size_t bytes, unsigned) { return cudaMalloc(p, bytes); }
-cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
+cudaError_t cudaFreeHost(void* p) { return cudaFree(p); }
 
 cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { memmove(dst, src, bytes); return cudaSuccess; }
 cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t s) {
@@ -366,23 +428,45 @@ cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEvent_t b) {
 	*ms = (float)(b->t_ms.load() - a->t_ms.load());
 	return cudaSuccess;
 }
-// CUDA IPC inside ONE process only (a handle is the pointer plus the pid): enough for the self-chain tests, where a GPU is
-// its own neighbour; one process per GPU (torchrun) is not emulated
+// CUDA IPC: a handle is {pointer, pid, memfd, length}.  Inside the exporting process it resolves to the pointer itself (the
+// self-chain tests, where a GPU is its own neighbour); from another process it maps the exporter's memfd (B200_EMU_SHM=1).
+namespace {
+struct IpcHandle { void* p; long long pid; long long len; int fd; };
+static_assert(sizeof(IpcHandle) <= sizeof(cudaIpcMemHandle_t), "ipc handle");
+}
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
 	memset(h, 0, sizeof(*h));
-	const long long pid = (long long)getpid();
-	memcpy(h->reserved, &p, sizeof(p));
-	memcpy(h->reserved + 8, &pid, sizeof(pid));
+	IpcHandle ih; ih.p = p; ih.pid = (long long)getpid(); ih.len = 0; ih.fd = -1;
+	{
+		std::lock_guard<std::mutex> lk(g_guard_m);
+		for (auto& a : g_shm) if (a.p == p && !a.imported) { ih.len = (long long)a.len; ih.fd = a.fd; }
+	}
+	memcpy(h->reserved, &ih, sizeof(ih));
 	return cudaSuccess;
 }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) {
-	long long pid = 0;
-	memcpy(&pid, h.reserved + 8, sizeof(pid));
-	if (pid != (long long)getpid()) return cudaErrorNotSupported;
-	memcpy(p, h.reserved, sizeof(*p));
+	IpcHandle ih;
+	memcpy(&ih, h.reserved, sizeof(ih));
+	if (ih.pid == (long long)getpid()) { *p = ih.p; return cudaSuccess; }
+	if (ih.fd < 0) return cudaErrorNotSupported;
+	char path[64];
+	snprintf(path, sizeof(path), "/proc/%lld/fd/%d", ih.pid, ih.fd);
+	const int fd = open(path, O_RDWR);
+	if (fd < 0) return cudaErrorInvalidValue;
+	void* q = mmap(nullptr, (size_t)ih.len, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+	close(fd);
+	if (q == MAP_FAILED) return cudaErrorMemoryAllocation;
+	std::lock_guard<std::mutex> lk(g_guard_m);
+	g_shm.push_back({q, (size_t)ih.len, -1, true});
+	*p = q;
 	return cudaSuccess;
 }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+	std::lock_guard<std::mutex> lk(g_guard_m);
+	for (size_t k = 0; k < g_shm.size(); k++)
+		if (g_shm[k].p == p && g_shm[k].imported) { munmap(p, g_shm[k].len); g_shm.erase(g_shm.begin() + k); break; }
+	return cudaSuccess;
+}
 
 // test hooks (not part of the C ABI of the product library)
 extern "C" long long b200_emu_s16_overflows(void) { return emu::g_s16_overflow.load(); }

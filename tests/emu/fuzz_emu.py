@@ -74,6 +74,9 @@ def run_case(b200, O, c):
         fr = np.zeros(j1 - j0 + 1, O.CELL); fc = np.zeros(i1 - i0 + 1, O.CELL)
         fr["h"] = -np.cumsum(rng.integers(0, 4, fr.size)); fr["x"] = fr["h"] - rng.integers(1, 9, fr.size)
         fc["h"] = -np.cumsum(rng.integers(0, 4, fc.size)); fc["x"] = fc["h"] - rng.integers(1, 9, fc.size)
+        if rng.random() < 0.4:                   # the lower right of a huge matrix: scores in the millions (s16 frame far from zero)
+            off = int(rng.choice([100_000, 3_000_000, 400_000_000]))
+            fr["h"] += off; fr["x"] += off; fc["h"] += off; fc["x"] += off
         fc[0] = fr[0]
         kw.update(first_row_init=b200.INIT_CUSTOM, first_col_init=b200.INIT_CUSTOM, first_row=fr, first_col=fc)
         okw.update(first_row=fr, first_col=fc)

@@ -5,6 +5,9 @@ automatic / narrow / one-slice-per-GPU chunking, and on repeated calls with diff
 blocks and of the shared running best).
 
   python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py
+
+MGPU_CHECK_BACKEND=gloo: the same script where no GPU exists, one process per EMULATED device (tests/emu/, B200_LIB pointing at
+the emulation build, B200_EMU_SHM=1 so that the exchange blocks are shared between the processes): tests/test_emu_cpu.py.
 """
 import os
 import sys
@@ -48,8 +51,18 @@ def assemble(pieces_per_rank, chunks, first_cell_rank=0):
 
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    gloo = os.environ.get("MGPU_CHECK_BACKEND", "nccl") == "gloo"
+    if gloo:
+        dist.init_process_group("gloo")
+    else:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def sync():
+        if not gloo:
+            torch.cuda.synchronize()
+        dist.barrier()
+
     b200 = load_package()
     only = os.environ.get("MGPU_CASES")
     ok = True
@@ -64,7 +77,7 @@ def main():
         for rep, (lo, hi) in enumerate(reps):
             a, b = synth.make_pair(m, n, [(int(m * lo), int(m * hi))], 0.05, 0.01, 0.01, 0, 77 + rep)
             al.set_sequences(a, b)
-            torch.cuda.synchronize(); dist.barrier()
+            sync()
             kw = dict(recurrence=rec, want_best_score=(rec == SW), prune=prune, mgpu=True, chunk_cols=chunk)
             if rec == NW:
                 kw.update(first_row_init=b200.INIT_GAPS, first_col_init=b200.INIT_GAPS)
@@ -73,7 +86,7 @@ def main():
             else:
                 kw.update(use_callbacks=False)
             r = al.align_partition(0, 0, m, n, **kw)
-            torch.cuda.synchronize(); dist.barrier()
+            sync()
             got = [None] * world
             dist.all_gather_object(got, dict(best=tuple(r["best"]), cells=r["cells"], rows=r["rows"] if arte else {},
                                              last_column=r["last_column"] if arte else None))
@@ -112,7 +125,7 @@ def main():
                   f"per-GPU max/mean={max(per) * world / max(cells, 1):.2f} vs {ref}: {'OK' if good else 'MISMATCH'}", flush=True)
             ok = ok and bool(good)
         al.close()
-    flag = torch.tensor([0 if ok else 1], device="cuda")
+    flag = torch.tensor([0 if ok else 1], device="cpu" if gloo else "cuda")
     dist.all_reduce(flag)
     dist.destroy_process_group()
     sys.exit(int(flag.item() != 0))

@@ -101,3 +101,17 @@ def test_drop_in_binary_full_pipeline(emu_lib):
     ids = [f + "test_full_pipeline_matches_reference[fast-sw_3k]", f + "test_full_pipeline_matches_reference[diag-sw_3k]",
            f + "test_full_pipeline_matches_reference[fast-sw_40k_pruning_ram]", f + "test_multi_gpu_pipeline_matches_reference[0,0-nw_global_20k]"]
     assert _run_gpu_tests(emu_lib, ids, None, preload=True, timeout=1500) == 4
+
+
+def test_one_process_per_device_chain_under_torchrun(emu_lib):
+    """tests/mgpu_check.py, the script tests/test_mgpu_gpu.py launches on 2 / 4 / 8 real GPUs, with two PROCESSES of one emulated
+    device each (gloo instead of NCCL; the exchange blocks are shared memory mapped through the emulation's CUDA IPC): border
+    stores, event words, job queues and the running best cross the process border as they cross NVLink."""
+    env = dict(os.environ)
+    env.update(B200_LIB=emu_lib, B200_EMU_SHM="1", B200_EMU_DEVICES="2", MGPU_CHECK_BACKEND="gloo", B200_WATCHDOG_S="60",
+               MGPU_CASES="sw_small_s16,sw_small_s32,nw_global_s32")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29700 + os.getpid() % 200), os.path.join(ROOT, "tests", "mgpu_check.py")]
+    p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert p.stdout.count(": OK") == 3 and "MISMATCH" not in p.stdout, p.stdout[-3000:]

@@ -29,7 +29,7 @@ def _run(exe, fa, fb, wd, extra, env=None):
     e = dict(os.environ)
     e.update(env or {})
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1200, env=e)
-    assert r.returncode == 0, f"{' '.join(cmd)}\n{r.stdout[-3000:]}"
+    assert r.returncode == 0, f"{' '.join(cmd)}\nexit code {r.returncode}\n{r.stdout[-3000:]}"
 
 
 _REF_CACHE = {}
