@@ -87,6 +87,11 @@ def load_library(path=None):
     if _lib is not None and path is None:
         return _lib
     lib = C.CDLL(path or LIB_PATH)
+    if hasattr(lib, "b200_emu_is_emulation") and os.environ.get("B200_TEST_EMULATION") != "1":
+        # tests/emu/ builds the same sources for the host CPU so that the test suite can exercise the device code without a
+        # GPU.  That build is test infrastructure: only a test run that says so may bind it.
+        raise OSError(f"{path or LIB_PATH} is the SIMT emulation build of the test suite, not libb200align.so: this package has "
+                      "no CPU path (tests set B200_TEST_EMULATION=1 to bind it)")
     lib.b200_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
     lib.b200_destroy.argtypes = [C.c_void_p]
     lib.b200_destroy.restype = None

@@ -128,6 +128,7 @@ def main():
     args = ap.parse_args()
     import build_emu
     os.environ["B200_LIB"] = build_emu.build()
+    os.environ["B200_TEST_EMULATION"] = "1"
     os.environ.setdefault("B200_WATCHDOG_S", "30")
     if args.shuffle:
         os.environ["B200_EMU_SHUFFLE"] = str(args.seed + 100)
