@@ -116,7 +116,6 @@ static inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int* n, 
 // ---------------------------------------------------------------------------------------------- SIMT execution
 namespace emu {
 
-struct ThreadIds { uint3 tid; };
 uint3& cur_thread_idx();
 extern thread_local uint3 t_blockIdx, t_blockDim, t_gridDim;
 

@@ -151,7 +151,10 @@ def main():
             bad += 1
             print(tag, "MISMATCH:", repr(e)[:400], f"   replay: --seed {args.seed} --only {k}", flush=True)
             break
-    print(f"fuzz: {args.cases if args.only < 0 else 1} cases, {bad} mismatches (seed {args.seed})")
+    import ctypes
+    ovf = b200.load_library().b200_emu_s16_overflows
+    ovf.restype = ctypes.c_longlong
+    print(f"fuzz: {args.cases if args.only < 0 else 1} cases, {bad} mismatches, {ovf()} s16 overflow events (seed {args.seed})")
     return 1 if bad else 0
 
 

@@ -125,3 +125,13 @@ def test_one_process_per_device_chain_under_torchrun(emu_lib):
     p = subprocess.run(cmd, cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:]
     assert p.stdout.count(": OK") == 3 and "MISMATCH" not in p.stdout, p.stdout[-3000:]
+
+
+def test_fuzz_sweep_against_the_oracle(emu_lib):
+    """A short fixed-seed sweep of tests/emu/fuzz_emu.py: random shapes around the tile boundaries, both kernels, SW / NW, every
+    border kind (also offset by millions), N / IUPAC bytes, pruning, self-chain and groups on distinct emulated devices -- bit-exact
+    against the oracle, and not one s16 overflow in the packed arithmetic."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_emu.py"), "--cases", "40", "--seed", "21", "--max-side", "1500"],
+                       cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:]
+    assert "fuzz: 40 cases, 0 mismatches, 0 s16 overflow events" in r.stdout, r.stdout[-1500:]
