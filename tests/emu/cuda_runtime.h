@@ -127,7 +127,7 @@ void poll_tick();                      // called by the polling loads: a spin lo
 int lane_id();
 char* smem_anchor();                   // any address inside this CTA's thread-local storage
 unsigned sm_id_of_block();
-void note_s16_overflow();
+void note_s16_overflow(int a, int b);
 
 cudaError_t launch(cudaStream_t s, dim3 grid, dim3 block, std::function<void()> body);
 template <class K, class... A>
@@ -231,7 +231,7 @@ static inline int emu_s16(unsigned v) { return (int)(short)(v & 0xffffu); }
 // logic must never let that happen for a value that matters -- B200_EMU_OVERFLOW counts the events, see emu_runtime.cpp)
 static inline unsigned emu_add16(int a, int b) {
 	const int s = a + b;
-	if (s > 32767 || s < -32768) emu::note_s16_overflow();
+	if (s > 32767 || s < -32768) emu::note_s16_overflow(a, b);
 	return (unsigned)s & 0xffffu;
 }
 static inline unsigned __vadd2(unsigned a, unsigned b) { return emu_add16(emu_s16(a), emu_s16(b)) | (emu_add16(emu_s16(a >> 16), emu_s16(b >> 16)) << 16); }

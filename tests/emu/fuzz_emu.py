@@ -137,6 +137,9 @@ def main():
     b200 = load_package()
     assert b200.load_library().b200_emu_is_emulation() == 1
     bad = 0
+    import ctypes
+    ovf = b200.load_library().b200_emu_s16_overflows
+    ovf.restype = ctypes.c_longlong
     for k in range(args.cases):
         rng = np.random.default_rng([args.seed, k])
         c = make_case(rng, args.max_side)
@@ -145,15 +148,13 @@ def main():
         tag = (f"case {k}: {c['m']}x{c['n']} {c['kernel']} {'NW' if c['nw'] else 'SW'} mode={c['mode']} world={c['world']} chunk={c['chunk']} "
                f"sub={int(c['sub'])} mixed={int(c['mixed'])} prune={int(c['prune'])} special={int(c['special'])}")
         try:
+            o0 = ovf()
             what = run_case(b200, O, c)
-            print(tag, "ok:", what, flush=True)
+            print(tag, "ok:", what, f"[{ovf() - o0} s16 overflow events]" if ovf() != o0 else "", flush=True)
         except Exception as e:                      # noqa: BLE001
             bad += 1
             print(tag, "MISMATCH:", repr(e)[:400], f"   replay: --seed {args.seed} --only {k}", flush=True)
             break
-    import ctypes
-    ovf = b200.load_library().b200_emu_s16_overflows
-    ovf.restype = ctypes.c_longlong
     print(f"fuzz: {args.cases if args.only < 0 else 1} cases, {bad} mismatches, {ovf()} s16 overflow events (seed {args.seed})")
     return 1 if bad else 0
 

@@ -130,8 +130,10 @@ def test_one_process_per_device_chain_under_torchrun(emu_lib):
 def test_fuzz_sweep_against_the_oracle(emu_lib):
     """A short fixed-seed sweep of tests/emu/fuzz_emu.py: random shapes around the tile boundaries, both kernels, SW / NW, every
     border kind (also offset by millions), N / IUPAC bytes, pruning, self-chain and groups on distinct emulated devices -- bit-exact
-    against the oracle, and not one s16 overflow in the packed arithmetic."""
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_emu.py"), "--cases", "40", "--seed", "21", "--max-side", "1500"],
+    against the oracle.  The sweep also counts s16 overflows of the packed arithmetic: the only ones this seed produces are the
+    16 of case 125 (dead lanes below the last row of a partial strip whose frame is ~ -32770: DESIGN.md section 7, item 7)."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "fuzz_emu.py"), "--cases", "150", "--seed", "21", "--max-side", "2500"],
                        cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:]
-    assert "fuzz: 40 cases, 0 mismatches, 0 s16 overflow events" in r.stdout, r.stdout[-1500:]
+    assert "fuzz: 150 cases, 0 mismatches, 16 s16 overflow events" in r.stdout, r.stdout[-1500:]
+    assert r.stdout.count("s16 overflow events]") == 1 and "case 125: 17155x512 s16x2 NW" in r.stdout
