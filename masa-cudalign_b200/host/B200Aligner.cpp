@@ -99,6 +99,7 @@ void B200Aligner::ensureGroup() {
 	b200_partition whole;
 	memset(&whole, 0, sizeof(whole));
 	whole.i1 = seq0_len; whole.j1 = seq1_len;
+	if (const char* e = getenv("B200_CHAIN_CHUNK")) whole.reserved[1] = atoi(e);   /* the chunk width override of alignPartitionFast (tests): size the exchange blocks for it */
 	b200_chain_info info;
 	const std::vector<int>& devs = params->getGpuList();
 	if (b200_chain_plan(&whole, (int)devs.size(), &info) != 0) { fprintf(stderr, "B200Aligner: b200_chain_plan failed\n"); exit(-1); }

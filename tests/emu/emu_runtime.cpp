@@ -20,6 +20,9 @@
 #include <thread>
 
 #include <execinfo.h>
+#if defined(__SANITIZE_ADDRESS__)
+#include <sanitizer/asan_interface.h>
+#endif
 #include <fcntl.h>
 #include <sched.h>
 #include <unistd.h>
@@ -151,6 +154,10 @@ void fiber_main() {
 
 void run_block(unsigned bidx, dim3 grid, dim3 block, const std::function<void()>& body, char* stacks, std::mt19937* rng) {
 	const int n = (int)block.x;
+#if defined(__SANITIZE_ADDRESS__)
+	// fibers never unwind (they end in a switch), so the redzones of their last frames would stay poisoned on a reused stack
+	__asan_unpoison_memory_region(stacks, (size_t)n * kStackBytes);
+#endif
 	Block b;
 	b.fibers.resize(n);
 	b.warps.resize((n + 31) / 32);
