@@ -46,7 +46,8 @@ GROUPS = {
                 "or test_self_chain_sw_matches_oracle[3000-3000 or test_group_on_one_device_sw[s16x2-4-700]", {"B200_EMU_SHUFFLE": "11"}, False),
     "pipeline": ([F_PIPE + "test_full_pipeline_matches_reference[fast-sw_3k]", F_PIPE + "test_full_pipeline_matches_reference[diag-sw_3k]",
                   F_PIPE + "test_full_pipeline_matches_reference[fast-sw_40k_pruning_ram]",
-                  F_PIPE + "test_multi_gpu_pipeline_matches_reference[0,0-nw_global_20k]"], None, {}, True),
+                  F_PIPE + "test_multi_gpu_pipeline_matches_reference[0,0-nw_global_20k]",
+                  F_PIPE + "test_multi_gpu_pipeline_with_narrow_chunks"], None, {}, True),
 }
 
 
@@ -147,7 +148,7 @@ def test_drop_in_binary_full_pipeline(runs):
     chain of two ranks."""
     if "pipeline" not in runs:
         pytest.skip("build/cudalign or oracle/_ref/oracle_cpu not built (they need the reference mount at build time)")
-    assert _passed(runs["pipeline"]) == 4
+    assert _passed(runs["pipeline"]) == 5
 
 
 def test_one_process_per_device_chain_under_torchrun(runs):
