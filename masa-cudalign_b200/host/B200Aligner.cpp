@@ -98,7 +98,8 @@ void B200Aligner::finalize() {
 void B200Aligner::ensureGroup() {
 	b200_partition whole;
 	memset(&whole, 0, sizeof(whole));
-	whole.i1 = seq0_len; whole.j1 = seq1_len;
+	/* MASA-Core hands over empty sequences for degenerate (pure-gap) stages of semi-global alignments: plan for one cell */
+	whole.i1 = seq0_len > 0 ? seq0_len : 1; whole.j1 = seq1_len > 0 ? seq1_len : 1;
 	if (const char* e = getenv("B200_CHAIN_CHUNK")) whole.reserved[1] = atoi(e);   /* the chunk width override of alignPartitionFast (tests): size the exchange blocks for it */
 	b200_chain_info info;
 	const std::vector<int>& devs = params->getGpuList();

@@ -47,9 +47,16 @@ def main():
             lo, hi = 0.1, 0.9
         a, b = synth.make_pair(m, n, [(int(m * lo), int(m * hi))], float(rng.choice([0.02, 0.05, 0.1])), 0.02, 0.02, int(rng.integers(0, 3)), int(rng.integers(1, 1 << 30)))
         extra = []
-        nw = rng.random() < 0.3
+        r_edges = rng.random()
+        nw = r_edges < 0.3
         if nw:
             extra += ["--alignment-edges=++"]
+        elif r_edges < 0.5:                      # one of the other 23 start/end rules (semi-global kinds, libmasa.cpp:258-264)
+            ed = "**"
+            while ed in ("**", "++"):
+                ed = str(rng.choice(list("*123+"))) + str(rng.choice(list("*123+")))
+            extra += [f"--alignment-edges={ed}"]
+            nw = True                            # (pruning is a stage-1 SW-local feature: keep it off for these)
         if nw or rng.random() < 0.5:
             extra += ["--no-block-pruning"]
         sra = str(rng.choice(["", "--ram-size=1M", "--disk-size=2M", "--ram-size=200K"]))

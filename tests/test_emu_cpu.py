@@ -47,7 +47,10 @@ GROUPS = {
     "pipeline": ([F_PIPE + "test_full_pipeline_matches_reference[fast-sw_3k]", F_PIPE + "test_full_pipeline_matches_reference[diag-sw_3k]",
                   F_PIPE + "test_full_pipeline_matches_reference[fast-sw_40k_pruning_ram]",
                   F_PIPE + "test_multi_gpu_pipeline_matches_reference[0,0-nw_global_20k]",
-                  F_PIPE + "test_multi_gpu_pipeline_with_narrow_chunks"], None, {}, True),
+                  "tests/test_xmodes_gpu.py::test_multi_gpu_pipeline_with_narrow_chunks",
+                  "tests/test_xmodes_gpu.py::test_alignment_edges_match_reference[*+]", "tests/test_xmodes_gpu.py::test_alignment_edges_match_reference[12]",
+                  "tests/test_xmodes_gpu.py::test_alignment_edges_match_reference[3+]", "tests/test_xmodes_gpu.py::test_alignment_edges_match_reference[21]"],
+                 None, {}, True),
 }
 
 
@@ -144,11 +147,11 @@ def test_scheduling_order_does_not_matter(runs):
 
 def test_drop_in_binary_full_pipeline(runs):
     """build/cudalign (B200Aligner + the reference's unmodified MASA-Core, stages 1-6, stage 4 and 5 substitutes) against the
-    reference's CPU run: crosspoint files, alignment.00.bin / .txt, special rows -- fast path, diag path, and stage 1 on a
-    chain of two ranks."""
+    reference's CPU run: crosspoint files, alignment.00.bin / .txt, special rows -- fast path, diag path, stage 1 on a chain of
+    two ranks, semi-global --alignment-edges modes, a chunk width far below the automatic one."""
     if "pipeline" not in runs:
         pytest.skip("build/cudalign or oracle/_ref/oracle_cpu not built (they need the reference mount at build time)")
-    assert _passed(runs["pipeline"]) == 5
+    assert _passed(runs["pipeline"]) == 9
 
 
 def test_one_process_per_device_chain_under_torchrun(runs):

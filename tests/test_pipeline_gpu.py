@@ -133,22 +133,3 @@ def test_multi_gpu_pipeline_matches_reference(tmp_path, tmp_path_factory, name, 
         assert nrows > 0
     assert "on the multi-GPU chain" in stats and " 0 of them on the multi-GPU chain" not in stats, "stage 1 did not take the chain"
 
-
-def test_multi_gpu_pipeline_with_narrow_chunks(tmp_path, tmp_path_factory):
-    """--gpus with a chunk width far below the automatic one: many more chain jobs per GPU than the default plan has.  The
-    adapter must size the exchange blocks for the width it is going to use (found by tests/emu/fuzz_pipeline.py: the group was
-    planned for the automatic width and the run refused with "more jobs than the exchange block was exported for")."""
-    _need_binaries()
-    m, n = 8192, 20000
-    a, b = synth.make_pair(m, n, [(1000, 7000)], 0.05, 0.02, 0.02, 0, 13)
-    fa, fb = str(tmp_path / "A.fa"), str(tmp_path / "B.fa")
-    synth.write_fasta(fa, a, "A")
-    synth.write_fasta(fb, b, "B")
-    extra = ["--no-block-pruning", "--disk-size=4M"]
-    w_new = str(tmp_path / "new")
-    w_ref = _ref_run(tmp_path_factory, "narrow_chunks", fa, fb, extra)
-    _run(CUDALIGN, fa, fb, w_new, extra + ["--gpus=0,0"],
-         env={"B200_GROUP_WARPS_PER_SM": "8", "B200_GROUP_MIN_CELLS": "0", "B200_CHAIN_CHUNK": "32", "B200_WATCHDOG_S": "30"})
-    _compare(w_ref, w_new, True)
-    stats = open(os.path.join(w_new, "statistics.ALIGNER")).read()
-    assert "on the multi-GPU chain" in stats and " 0 of them on the multi-GPU chain" not in stats, "stage 1 did not take the chain"
