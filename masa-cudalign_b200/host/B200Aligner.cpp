@@ -144,8 +144,30 @@ match_result_t B200Aligner::matchLastColumn(const cell_t* buffer, const cell_t* 
 /* ------------------------------------------------------------------------------------------------------------
  * B200-first path for stage 1
  * ---------------------------------------------------------------------------------------------------------- */
+/* --dump-blocks (C/libmasa/libmasa.cpp:1082, C/stage1/sw_stage1.cpp:310-314) makes the manager file the score of EVERY block of
+ * the reference's grid (AlignerManager.cpp:418-422) -- a per-block artefact only the per-diagonal path produces.  The flag is
+ * MASA-Core's own (the aligner is never told: IManager has no query for it), so the adapter looks at the command line. */
+static bool dumpBlocksRequested() {
+	static int cached = -1;
+	if (cached < 0) {
+		cached = 0;
+		FILE* f = fopen("/proc/self/cmdline", "rb");
+		if (f != NULL) {
+			std::string all;
+			char buf[4096];
+			size_t got;
+			while ((got = fread(buf, 1, sizeof(buf), f)) > 0) all.append(buf, got);
+			fclose(f);
+			for (size_t pos = 0; pos < all.size(); pos += strlen(all.c_str() + pos) + 1)
+				if (strcmp(all.c_str() + pos, "--dump-blocks") == 0) cached = 1;
+		}
+	}
+	return cached == 1;
+}
+
 bool B200Aligner::canUseFastPath() {
 	if (!params->useFastPath()) return false;
+	if (dumpBlocksRequested()) return false;          /* per-block scores: the reference's per-diagonal contract */
 	if (mustDispatchLastColumn()) return false;      /* stages 2/3 (goal matching, early stop), split partitions */
 	if (mustDispatchSpecialColumns()) return false;
 	return true;

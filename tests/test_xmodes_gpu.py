@@ -2,9 +2,9 @@
 the semi-global kinds, C/libmasa/libmasa.cpp:258-264) and --gpus with a chunk width far below the automatic one.
 
 Both groups come from the differential fuzzing on the SIMT emulation (tests/emu/fuzz_pipeline.py, profiles/r02_emu_fuzz.txt), which
-found two refusals of build/cudalign --gpus: empty sequences handed over by MASA-Core for the degenerate stages of a semi-global
+found two refusals of build/cudalign --gpus -- empty sequences handed over by MASA-Core for the degenerate stages of a semi-global
 alignment ("b200_chain_plan failed"), and exchange blocks planned for the automatic chunk width while the B200_CHAIN_CHUNK
-override was in force.  The file is named to be collected last: it was written after the round's last GPU run and has run on the
+override was in force -- and --dump-blocks failing on the fast path.  The file is named to be collected last: it was written after the round's last GPU run and has run on the
 emulation only (tests/test_emu_cpu.py), so under `pytest -x` it cannot hide the tests that have run on the B200."""
 import os
 import sys
@@ -67,3 +67,18 @@ def test_multi_gpu_pipeline_with_narrow_chunks(tmp_path, tmp_path_factory):
     P._compare(w_ref, w_new, True)
     stats = open(os.path.join(w_new, "statistics.ALIGNER")).read()
     assert "on the multi-GPU chain" in stats and " 0 of them on the multi-GPU chain" not in stats, "stage 1 did not take the chain"
+
+
+@pytest.mark.parametrize("mode", ["single", "gpus"])
+def test_dump_blocks_takes_the_per_diagonal_path(tmp_path, tmp_path_factory, pair, mode):
+    """--dump-blocks wants the score of every block of the reference's grid (AlignerManager.cpp:418-422, sw_stage1.cpp:310-314): the
+    whole-partition kernel has no such artefact, so the adapter must fall back to the per-diagonal path -- pruning_dump.txt and the
+    alignment (which embeds it, sw_stage5.cpp:456) identical to the reference's.  (Found on the emulation: the fast path exited 1.)"""
+    P._need_binaries()
+    fa, fb = pair
+    extra = ["--dump-blocks", "--disk-size=1M"]
+    w_ref = P._ref_run(tmp_path_factory, "dump_blocks", fa, fb, extra)
+    w_new = str(tmp_path / "new")
+    P._run(P.CUDALIGN, fa, fb, w_new, extra + (["--gpus=0,0"] if mode == "gpus" else []), env=CHAIN_ENV)
+    P._compare(w_ref, w_new, False)
+    assert open(os.path.join(w_ref, "pruning_dump.txt"), "rb").read() == open(os.path.join(w_new, "pruning_dump.txt"), "rb").read()
