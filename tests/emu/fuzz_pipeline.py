@@ -46,7 +46,16 @@ def main():
         if hi - lo < 0.2:
             lo, hi = 0.1, 0.9
         a, b = synth.make_pair(m, n, [(int(m * lo), int(m * hi))], float(rng.choice([0.02, 0.05, 0.1])), 0.02, 0.02, int(rng.integers(0, 3)), int(rng.integers(1, 1 << 30)))
+        if rng.random() < 0.25:                  # N / IUPAC / lower-case bytes: the byte-compare semantics of the reference (mixed kernels)
+            for sq in (a, b):
+                cnt = int(rng.integers(1, max(2, sq.size // 40)))
+                sq[rng.integers(0, sq.size, cnt)] = rng.choice(np.frombuffer(b"NNNRYKMacgtn", np.uint8), cnt)
+                if sq.size > 400:
+                    p0 = int(rng.integers(0, sq.size - 300))
+                    sq[p0:p0 + int(rng.integers(10, 300))] = ord("N")
         extra = []
+        if rng.random() < 0.15:
+            extra.append("--clear-n")
         r_edges = rng.random()
         nw = r_edges < 0.3
         if nw:
